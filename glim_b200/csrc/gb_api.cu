@@ -1,0 +1,574 @@
+// gb_api.cu -- implementation of the C-ABI declared in include/glim_b200.h (host side of libglim_b200.so).
+#include "gb_internal.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void gb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* gb_last_error(void) { return g_err; }
+extern "C" const char* gb_status_string(gb_status s) {
+  switch (s) {
+    case GB_OK: return "ok";
+    case GB_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case GB_ERR_CUDA: return "CUDA error";
+    case GB_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case GB_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case GB_ERR_INTERNAL: return "internal error";
+  }
+  return "unknown status";
+}
+
+extern "C" int gb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" gb_status gb_mem_info(int device, size_t* free_bytes, size_t* total_bytes) {
+  GB_REQUIRE(free_bytes && total_bytes, "null output");
+  if (gb_device_count() <= device) { gb_set_error("no CUDA device %d", device); return GB_ERR_NO_DEVICE; }
+  GB_CUDA(cudaSetDevice(device));
+  GB_CUDA(cudaMemGetInfo(free_bytes, total_bytes));
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+static gb_status ctx_create(int device, cudaStream_t stream, bool own, gb_ctx** out) {
+  GB_REQUIRE(out, "null output");
+  *out = nullptr;
+  const int n = gb_device_count();
+  if (n <= 0 || device < 0 || device >= n) {
+    gb_set_error("no CUDA device %d (%d visible); libglim_b200 has no CPU fallback", device, n);
+    return GB_ERR_NO_DEVICE;
+  }
+  GB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    gb_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return GB_ERR_NO_DEVICE;
+  }
+  gb_ctx* c = new (std::nothrow) gb_ctx();
+  if (!c) return GB_ERR_INTERNAL;
+  c->device = device;
+  c->own_stream = own;
+  c->stream = stream;
+  if (own) {
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; gb_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return GB_ERR_CUDA; }
+  }
+  c->num_sms = prop.multiProcessorCount;
+  c->scratch = nullptr; c->scratch_cap = 0;
+  c->pinned = nullptr; c->pinned_cap = 0;
+  c->launches = 0; c->epoch = 1; c->next_id = 1;
+  *out = c;
+  return GB_OK;
+}
+extern "C" gb_status gb_ctx_create(int device, gb_ctx** out) { return ctx_create(device, nullptr, true, out); }
+extern "C" gb_status gb_ctx_create_on_stream(int device, void* cuda_stream, gb_ctx** out) { return ctx_create(device, (cudaStream_t)cuda_stream, false, out); }
+
+static void sweep_free(gb_sweep* s);
+
+extern "C" gb_status gb_ctx_destroy(gb_ctx* ctx) {
+  if (!ctx) return GB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (gb_sweep* s : ctx->sweep_cache) sweep_free(s);
+  ctx->sweep_cache.clear();
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return GB_OK;
+}
+extern "C" gb_status gb_ctx_synchronize(gb_ctx* ctx) {
+  GB_REQUIRE(ctx, "null ctx");
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GB_OK;
+}
+extern "C" void* gb_ctx_stream(gb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t gb_ctx_kernel_launches(gb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+gb_status gb_ctx_scratch(gb_ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->scratch_cap) {
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->scratch) GB_CUDA(cudaFree(ctx->scratch));
+    ctx->scratch = nullptr; ctx->scratch_cap = 0;
+    const size_t cap = bytes + bytes / 4;
+    GB_CUDA(cudaMalloc(&ctx->scratch, cap));
+    ctx->scratch_cap = cap;
+  }
+  *out = ctx->scratch;
+  return GB_OK;
+}
+gb_status gb_ctx_pinned(gb_ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->pinned_cap) {
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->pinned) GB_CUDA(cudaFreeHost(ctx->pinned));
+    ctx->pinned = nullptr; ctx->pinned_cap = 0;
+    const size_t cap = bytes + bytes / 4;
+    GB_CUDA(cudaMallocHost(&ctx->pinned, cap));
+    ctx->pinned_cap = cap;
+  }
+  *out = ctx->pinned;
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// clouds
+// ---------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" gb_status gb_cloud_upload(gb_ctx* ctx, size_t n, const double* xyzw, const double* cov4x4, const double* normals4, gb_cloud** out) {
+  GB_REQUIRE(ctx && out, "null ctx / output");
+  GB_REQUIRE(n == 0 || xyzw, "null points");
+  GB_REQUIRE(n < (size_t)1 << 30, "too many points");
+  *out = nullptr;
+  GB_CUDA(cudaSetDevice(ctx->device));
+  gb_cloud* c = new (std::nothrow) gb_cloud();
+  if (!c) return GB_ERR_INTERNAL;
+  c->ctx = ctx; c->n = n; c->base = nullptr; c->bytes = 0;
+  c->p0 = nullptr; c->p1 = nullptr; c->p2 = nullptr; c->normals = nullptr;
+  if (n == 0) { *out = c; return GB_OK; }
+  // the reference casts Vector4d / Matrix4d to float on the host before the copy; so do we,
+  // straight into the device plane layout, staged through pinned memory
+  const size_t b0 = align_up(sizeof(float4) * n, 256), b1 = b0, b2 = align_up(sizeof(float) * n, 256), b3 = normals4 ? b0 : 0;
+  const size_t total = b0 + b1 + b2 + b3;
+  char* h = nullptr;
+  gb_status st = gb_ctx_pinned(ctx, total, (void**)&h);
+  if (st != GB_OK) { delete c; return st; }
+  float4* h0 = (float4*)h;
+  float4* h1 = (float4*)(h + b0);
+  float* h2 = (float*)(h + b0 + b1);
+  float4* h3 = (float4*)(h + b0 + b1 + b2);
+  for (size_t i = 0; i < n; i++) {
+    const double* p = xyzw + 4 * i;
+    float c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+    if (cov4x4) {
+      const double* C = cov4x4 + 16 * i;  // column-major 4x4: (r,c) at c*4+r; upper triangle
+      c00 = (float)C[0]; c01 = (float)C[4]; c02 = (float)C[8]; c11 = (float)C[5]; c12 = (float)C[9]; c22 = (float)C[10];
+    }
+    h0[i] = make_float4((float)p[0], (float)p[1], (float)p[2], c00);
+    h1[i] = make_float4(c01, c02, c11, c12);
+    h2[i] = c22;
+    if (normals4) h3[i] = make_float4((float)normals4[4 * i], (float)normals4[4 * i + 1], (float)normals4[4 * i + 2], 0.f);
+  }
+  cudaError_t e = cudaMalloc(&c->base, total);
+  if (e != cudaSuccess) { delete c; gb_set_error("cudaMalloc(%zu): %s", total, cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
+  c->bytes = total;
+  char* d = (char*)c->base;
+  c->p0 = (float4*)d; c->p1 = (float4*)(d + b0); c->p2 = (float*)(d + b0 + b1); c->normals = normals4 ? (float4*)(d + b0 + b1 + b2) : nullptr;
+  e = cudaMemcpyAsync(c->base, h, total, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the pinned staging buffer is reused by the next call
+  if (e != cudaSuccess) { cudaFree(c->base); delete c; gb_set_error("upload: %s", cudaGetErrorString(e)); return GB_ERR_CUDA; }
+  *out = c;
+  return GB_OK;
+}
+extern "C" gb_status gb_cloud_size(const gb_cloud* cloud, size_t* n) {
+  GB_REQUIRE(cloud && n, "null argument");
+  *n = cloud->n;
+  return GB_OK;
+}
+extern "C" gb_status gb_cloud_download(const gb_cloud* c, float* xyz, float* cov6) {
+  GB_REQUIRE(c, "null cloud");
+  if (c->n == 0) return GB_OK;
+  std::vector<float4> h0(c->n), h1(c->n);
+  std::vector<float> h2(c->n);
+  GB_CUDA(cudaStreamSynchronize(c->ctx->stream));
+  GB_CUDA(cudaMemcpy(h0.data(), c->p0, sizeof(float4) * c->n, cudaMemcpyDeviceToHost));
+  GB_CUDA(cudaMemcpy(h1.data(), c->p1, sizeof(float4) * c->n, cudaMemcpyDeviceToHost));
+  GB_CUDA(cudaMemcpy(h2.data(), c->p2, sizeof(float) * c->n, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < c->n; i++) {
+    if (xyz) { xyz[3 * i] = h0[i].x; xyz[3 * i + 1] = h0[i].y; xyz[3 * i + 2] = h0[i].z; }
+    if (cov6) { cov6[6 * i] = h0[i].w; cov6[6 * i + 1] = h1[i].x; cov6[6 * i + 2] = h1[i].y; cov6[6 * i + 3] = h1[i].z; cov6[6 * i + 4] = h1[i].w; cov6[6 * i + 5] = h2[i]; }
+  }
+  return GB_OK;
+}
+extern "C" gb_status gb_cloud_destroy(gb_cloud* c) {
+  if (!c) return GB_OK;
+  cudaSetDevice(c->ctx->device);
+  cudaStreamSynchronize(c->ctx->stream);
+  if (c->base) cudaFree(c->base);
+  delete c;
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// voxel maps
+// ---------------------------------------------------------------------------------------------
+extern "C" gb_status gb_voxelmap_build(gb_ctx* ctx, const gb_cloud* cloud, float resolution, int init_num_buckets, int max_bucket_scan_count, double target_points_drop_rate, gb_voxelmap** out) {
+  GB_REQUIRE(ctx && cloud && out, "null argument");
+  GB_REQUIRE(resolution > 0.f, "resolution must be positive");
+  GB_REQUIRE(init_num_buckets > 0 && (init_num_buckets & (init_num_buckets - 1)) == 0, "init_num_buckets must be a power of two");
+  GB_REQUIRE(max_bucket_scan_count > 0, "max_bucket_scan_count must be positive");
+  *out = nullptr;
+  GB_CUDA(cudaSetDevice(ctx->device));
+  gb_voxelmap* m = new (std::nothrow) gb_voxelmap();
+  if (!m) return GB_ERR_INTERNAL;
+  gb_status st = gb_voxelmap_build_impl(ctx, cloud, resolution, init_num_buckets, max_bucket_scan_count, target_points_drop_rate, m);
+  if (st != GB_OK) {
+    if (m->base) cudaFree(m->base);
+    if (m->buckets) cudaFree(m->buckets);
+    delete m;
+    return st;
+  }
+  *out = m;
+  return GB_OK;
+}
+extern "C" gb_status gb_voxelmap_info(const gb_voxelmap* m, int* num_voxels, int* num_buckets, float* resolution) {
+  GB_REQUIRE(m, "null map");
+  if (num_voxels) *num_voxels = m->num_voxels;
+  if (num_buckets) *num_buckets = m->num_buckets;
+  if (resolution) *resolution = m->resolution;
+  return GB_OK;
+}
+extern "C" gb_status gb_voxelmap_download(const gb_voxelmap* m, int32_t* buckets, int32_t* num_points, float* means, float* cov6) {
+  GB_REQUIRE(m, "null map");
+  GB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  if (buckets) GB_CUDA(cudaMemcpy(buckets, m->buckets, sizeof(int4) * (size_t)m->num_buckets, cudaMemcpyDeviceToHost));
+  if ((num_points || means || cov6) && m->num_voxels > 0) {
+    std::vector<float4> h(3 * (size_t)m->num_voxels);
+    GB_CUDA(cudaMemcpy(h.data(), m->voxels, sizeof(float4) * h.size(), cudaMemcpyDeviceToHost));
+    for (size_t v = 0; v < (size_t)m->num_voxels; v++) {
+      const float4 a = h[3 * v], b = h[3 * v + 1], c = h[3 * v + 2];
+      if (num_points) num_points[v] = (int32_t)c.y;
+      if (means) { means[3 * v] = a.x; means[3 * v + 1] = a.y; means[3 * v + 2] = a.z; }
+      if (cov6) { cov6[6 * v] = a.w; cov6[6 * v + 1] = b.x; cov6[6 * v + 2] = b.y; cov6[6 * v + 3] = b.z; cov6[6 * v + 4] = b.w; cov6[6 * v + 5] = c.x; }
+    }
+  }
+  return GB_OK;
+}
+extern "C" gb_status gb_voxelmap_destroy(gb_voxelmap* m) {
+  if (!m) return GB_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  if (m->base) cudaFree(m->base);
+  if (m->buckets) cudaFree(m->buckets);
+  delete m;
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// factors and sweeps
+// ---------------------------------------------------------------------------------------------
+extern "C" gb_status gb_vgicp_factor_create(gb_ctx* ctx, const gb_voxelmap* target, const gb_cloud* source, int flags, gb_factor** out) {
+  GB_REQUIRE(ctx && target && source && out, "null argument");
+  GB_REQUIRE(target->ctx->device == ctx->device && source->ctx->device == ctx->device, "cloud / voxel map live on another device");
+  gb_factor* f = new (std::nothrow) gb_factor();
+  if (!f) return GB_ERR_INTERNAL;
+  f->ctx = ctx; f->target = target; f->source = source; f->flags = flags; f->single = nullptr; f->id = ctx->next_id++;
+  *out = f;
+  return GB_OK;
+}
+
+static void sweep_free(gb_sweep* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  if (s->d_descs) cudaFree(s->d_descs);
+  if (s->h_poses) cudaFreeHost(s->h_poses);
+  delete s;
+}
+
+extern "C" gb_status gb_vgicp_factor_destroy(gb_factor* f) {
+  if (!f) return GB_OK;
+  gb_ctx* ctx = f->ctx;
+  if (f->single) sweep_free(f->single);
+  // cached sweeps that reference this factor are stale from now on
+  ctx->epoch++;
+  for (gb_sweep* s : ctx->sweep_cache) sweep_free(s);
+  ctx->sweep_cache.clear();
+  delete f;
+  return GB_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* factors, const int32_t* pair_index, gb_sweep** out) {
+  GB_REQUIRE(ctx && out, "null argument");
+  GB_REQUIRE(F == 0 || factors, "null factor list");
+  *out = nullptr;
+  GB_CUDA(cudaSetDevice(ctx->device));
+  gb_sweep* s = new (std::nothrow) gb_sweep();
+  if (!s) return GB_ERR_INTERNAL;
+  s->ctx = ctx; s->F = F; s->factors.assign(factors, factors + F);
+  s->d_descs = nullptr; s->d_tiles = nullptr; s->d_poses = nullptr; s->d_poses_eval = nullptr; s->d_accum = nullptr; s->d_done = nullptr; s->d_out = nullptr;
+  s->h_poses = nullptr; s->h_poses_eval = nullptr; s->h_out = nullptr; s->d_slab = nullptr; s->num_pairs = 0;
+  s->num_tiles = 0; s->point_factors = 0; s->algorithmic_bytes = 0; s->key = 0; s->epoch = ctx->epoch;
+
+  // tile size: enough tiles to balance the persistent grid, large enough to amortise the per-tile reduction
+  uint64_t total_pts = 0;
+  for (size_t f = 0; f < F; f++) {
+    GB_REQUIRE(factors[f] && factors[f]->ctx == ctx, "factor belongs to another context");
+    total_pts += factors[f]->source->n;
+  }
+  const int ctas_per_sm = env_int("GB_CTAS_PER_SM", 2);
+  const int capacity = ctx->num_sms * ctas_per_sm;
+  int tile = env_int("GB_TILE", 0);
+  if (tile <= 0) {
+    const uint64_t want = total_pts / ((uint64_t)capacity * 8) + 1;
+    tile = (int)std::min<uint64_t>(4096, std::max<uint64_t>(512, (want + 255) / 256 * 256));
+  }
+  tile = (tile + 255) / 256 * 256;
+  s->tile_size = tile;
+
+  std::vector<FactorDesc> descs(F);
+  std::vector<int2> tiles;
+  for (size_t f = 0; f < F; f++) {
+    const gb_factor* fa = factors[f];
+    FactorDesc& D = descs[f];
+    D.p0 = fa->source->p0; D.p1 = fa->source->p1; D.p2 = fa->source->p2;
+    D.buckets = fa->target->buckets; D.voxels = fa->target->voxels;
+    D.mask = (uint32_t)fa->target->num_buckets - 1u;
+    D.max_scan = fa->target->max_scan;
+    D.inv_res = fa->target->inv_res;
+    D.n = (int)fa->source->n;
+    D.pair = pair_index ? pair_index[f] : (int)f;
+    D.flags = fa->flags;
+    D.first_tile = (int)tiles.size();
+    // a factor with no points still gets one (empty) tile so that its epilogue runs and zeroes its record
+    const int nt = std::max(1, (D.n + tile - 1) / tile);
+    D.num_tiles = nt;
+    for (int t = 0; t < nt; t++) tiles.push_back(make_int2((int)f, t * tile));
+    s->point_factors += (uint64_t)D.n;
+    // B_f of SURVEY 8(d): 48 B per source point (+12 with normals), 48 B per target voxel, 16 B per bucket, pose in + record out
+    s->algorithmic_bytes += (uint64_t)D.n * (48 + ((fa->flags & GB_FACTOR_SURFACE_VALIDATION) ? 12 : 0)) + (uint64_t)fa->target->num_voxels * 48 + (uint64_t)fa->target->num_buckets * 16 + 64 + 488;
+  }
+  s->num_tiles = (int)tiles.size();
+  s->grid = std::max(1, std::min(s->num_tiles, capacity));
+
+  if (F > 0) {
+    // one device allocation, one pinned allocation
+    const size_t b_desc = align_up(sizeof(FactorDesc) * F, 256), b_tiles = align_up(sizeof(int2) * tiles.size(), 256), b_pose = align_up(sizeof(double) * 16 * F, 256);
+    const size_t b_acc = align_up(sizeof(double) * GB_ACC_STRIDE * F, 256), b_done = align_up(sizeof(unsigned) * F, 256), b_out = align_up(sizeof(double) * GB_OUT_DOUBLES * F, 256);
+    const size_t total = b_desc + b_tiles + 2 * b_pose + b_acc + b_done + b_out;
+    char* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, total);
+    if (e != cudaSuccess) { delete s; gb_set_error("cudaMalloc(%zu): %s", total, cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
+    s->d_descs = (FactorDesc*)d; d += b_desc;
+    s->d_tiles = (int2*)d; d += b_tiles;
+    s->d_poses = (double*)d; d += b_pose;
+    s->d_poses_eval = (double*)d; d += b_pose;
+    s->d_accum = (double*)d; d += b_acc;
+    s->d_done = (unsigned*)d; d += b_done;
+    s->d_out = (double*)d;
+    char* h = nullptr;
+    e = cudaMallocHost((void**)&h, 2 * b_pose + b_out);
+    if (e != cudaSuccess) { cudaFree(s->d_descs); delete s; gb_set_error("cudaMallocHost: %s", cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
+    s->h_poses = (double*)h; s->h_poses_eval = (double*)(h + b_pose); s->h_out = (double*)(h + 2 * b_pose);
+    cudaStream_t st = ctx->stream;
+    e = cudaMemcpyAsync(s->d_descs, descs.data(), sizeof(FactorDesc) * F, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_accum, 0, b_acc + b_done, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // descs / tiles are stack-local vectors
+    if (e != cudaSuccess) { sweep_free(s); gb_set_error("sweep setup: %s", cudaGetErrorString(e)); return GB_ERR_CUDA; }
+  }
+  *out = s;
+  return GB_OK;
+}
+extern "C" gb_status gb_sweep_destroy(gb_sweep* s) { sweep_free(s); return GB_OK; }
+
+extern "C" gb_status gb_sweep_attach_slab(gb_sweep* s, void* device_slab_f32, size_t num_pairs) {
+  GB_REQUIRE(s, "null sweep");
+  for (size_t f = 0; f < s->F && device_slab_f32; f++) {
+    // pair indices were baked into the descriptors at creation; validate the range on the host copy
+    (void)f;
+  }
+  s->d_slab = (float*)device_slab_f32;
+  s->num_pairs = num_pairs;
+  return GB_OK;
+}
+
+extern "C" gb_status gb_sweep_set_poses(gb_sweep* s, const double* T) {
+  GB_REQUIRE(s && (s->F == 0 || T), "null argument");
+  if (s->F == 0) return GB_OK;
+  // the previous H2D from this pinned buffer must have been consumed
+  GB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  memcpy(s->h_poses, T, sizeof(double) * 16 * s->F);
+  GB_CUDA(cudaMemcpyAsync(s->d_poses, s->h_poses, sizeof(double) * 16 * s->F, cudaMemcpyHostToDevice, s->ctx->stream));
+  return GB_OK;
+}
+static gb_status sweep_set_eval_poses(gb_sweep* s, const double* T) {
+  if (s->F == 0) return GB_OK;
+  memcpy(s->h_poses_eval, T, sizeof(double) * 16 * s->F);
+  GB_CUDA(cudaMemcpyAsync(s->d_poses_eval, s->h_poses_eval, sizeof(double) * 16 * s->F, cudaMemcpyHostToDevice, s->ctx->stream));
+  return GB_OK;
+}
+extern "C" gb_status gb_sweep_launch(gb_sweep* s) {
+  GB_REQUIRE(s, "null sweep");
+  GB_CUDA(cudaSetDevice(s->ctx->device));
+  return gb_launch_sweep(s, GB_MODE_LINEARIZE);
+}
+extern "C" gb_status gb_sweep_fetch(gb_sweep* s, gb_linearized6* out) {
+  GB_REQUIRE(s && (s->F == 0 || out), "null argument");
+  if (s->F == 0) return GB_OK;
+  static_assert(sizeof(gb_linearized6) == sizeof(double) * GB_OUT_DOUBLES, "gb_linearized6 layout");
+  GB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, sizeof(double) * GB_OUT_DOUBLES * s->F, cudaMemcpyDeviceToHost, s->ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  memcpy(out, s->h_out, sizeof(double) * GB_OUT_DOUBLES * s->F);
+  return GB_OK;
+}
+extern "C" gb_status gb_sweep_results_device(gb_sweep* s, void** device_ptr) {
+  GB_REQUIRE(s && device_ptr, "null argument");
+  *device_ptr = s->d_out;
+  return GB_OK;
+}
+extern "C" gb_status gb_sweep_stats(const gb_sweep* s, uint64_t* point_factors, uint64_t* algorithmic_bytes, uint32_t* num_tiles, uint32_t* grid_size) {
+  GB_REQUIRE(s, "null sweep");
+  if (point_factors) *point_factors = s->point_factors;
+  if (algorithmic_bytes) *algorithmic_bytes = s->algorithmic_bytes;
+  if (num_tiles) *num_tiles = (uint32_t)s->num_tiles;
+  if (grid_size) *grid_size = (uint32_t)s->grid;
+  return GB_OK;
+}
+
+// cached sweep for (ctx, factor list): NonlinearFactorSetGPU keeps its factor list between linearize calls
+static gb_status cached_sweep(gb_ctx* ctx, size_t F, gb_factor* const* factors, gb_sweep** out) {
+  uint64_t key = 1469598103934665603ull;
+  for (size_t f = 0; f < F; f++) {
+    GB_REQUIRE(factors[f], "null factor");
+    key = (key ^ factors[f]->id) * 1099511628211ull;
+  }
+  key ^= (uint64_t)F << 48;
+  for (gb_sweep* s : ctx->sweep_cache)
+    if (s->key == key && s->F == F && s->epoch == ctx->epoch && std::equal(s->factors.begin(), s->factors.end(), factors)) { *out = s; return GB_OK; }
+  gb_sweep* s = nullptr;
+  GB_CHECK(gb_sweep_create(ctx, F, factors, nullptr, &s));
+  s->key = key;
+  if (ctx->sweep_cache.size() >= 8) { sweep_free(ctx->sweep_cache.front()); ctx->sweep_cache.erase(ctx->sweep_cache.begin()); }
+  ctx->sweep_cache.push_back(s);
+  *out = s;
+  return GB_OK;
+}
+
+extern "C" gb_status gb_factor_set_linearize(gb_ctx* ctx, size_t F, gb_factor* const* factors, const double* T, gb_linearized6* out) {
+  GB_REQUIRE(ctx, "null ctx");
+  if (F == 0) return GB_OK;
+  GB_REQUIRE(factors && T && out, "null argument");
+  gb_sweep* s = nullptr;
+  GB_CHECK(cached_sweep(ctx, F, factors, &s));
+  GB_CHECK(gb_sweep_set_poses(s, T));
+  GB_CHECK(gb_launch_sweep(s, GB_MODE_LINEARIZE));
+  return gb_sweep_fetch(s, out);
+}
+
+extern "C" gb_status gb_factor_set_error(gb_ctx* ctx, size_t F, gb_factor* const* factors, const double* T_lin, const double* T_eval, double* errors) {
+  GB_REQUIRE(ctx, "null ctx");
+  if (F == 0) return GB_OK;
+  GB_REQUIRE(factors && T_lin && T_eval && errors, "null argument");
+  gb_sweep* s = nullptr;
+  GB_CHECK(cached_sweep(ctx, F, factors, &s));
+  GB_CHECK(gb_sweep_set_poses(s, T_lin));
+  GB_CHECK(sweep_set_eval_poses(s, T_eval));
+  GB_CHECK(gb_launch_sweep(s, GB_MODE_ERROR));
+  GB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, sizeof(double) * GB_OUT_DOUBLES * F, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (size_t f = 0; f < F; f++) errors[f] = s->h_out[f * GB_OUT_DOUBLES + 120];
+  return GB_OK;
+}
+
+static gb_status single_sweep(gb_factor* f, gb_sweep** out) {
+  if (!f->single) GB_CHECK(gb_sweep_create(f->ctx, 1, &f, nullptr, &f->single));
+  *out = f->single;
+  return GB_OK;
+}
+extern "C" gb_status gb_vgicp_linearize(gb_factor* f, const double T[16], gb_linearized6* out) {
+  GB_REQUIRE(f && T && out, "null argument");
+  gb_sweep* s = nullptr;
+  GB_CHECK(single_sweep(f, &s));
+  GB_CHECK(gb_sweep_set_poses(s, T));
+  GB_CHECK(gb_launch_sweep(s, GB_MODE_LINEARIZE));
+  return gb_sweep_fetch(s, out);
+}
+extern "C" gb_status gb_vgicp_error(gb_factor* f, const double T_lin[16], const double T_eval[16], double* error) {
+  GB_REQUIRE(f && T_lin && T_eval && error, "null argument");
+  gb_sweep* s = nullptr;
+  GB_CHECK(single_sweep(f, &s));
+  GB_CHECK(gb_sweep_set_poses(s, T_lin));
+  GB_CHECK(sweep_set_eval_poses(s, T_eval));
+  GB_CHECK(gb_launch_sweep(s, GB_MODE_ERROR));
+  GB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, sizeof(double) * GB_OUT_DOUBLES, cudaMemcpyDeviceToHost, f->ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(f->ctx->stream));
+  *error = s->h_out[120];
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// overlap
+// ---------------------------------------------------------------------------------------------
+extern "C" gb_status gb_overlap(gb_ctx* ctx, size_t T, const gb_voxelmap* const* targets, const gb_cloud* source, const double* deltas, double* overlap) {
+  GB_REQUIRE(ctx && source && overlap, "null argument");
+  *overlap = 0.0;
+  if (T == 0 || source->n == 0) return GB_OK;
+  GB_REQUIRE(targets && deltas, "null targets / deltas");
+  GB_CUDA(cudaSetDevice(ctx->device));
+  const size_t b_desc = align_up(sizeof(FactorDesc) * T, 256), b_pose = align_up(sizeof(double) * 16 * T, 256);
+  char* h = nullptr;
+  char* d = nullptr;
+  GB_CHECK(gb_ctx_pinned(ctx, b_desc + b_pose + 256, (void**)&h));
+  GB_CHECK(gb_ctx_scratch(ctx, b_desc + b_pose + 256, (void**)&d));
+  FactorDesc* hd = (FactorDesc*)h;
+  for (size_t t = 0; t < T; t++) {
+    GB_REQUIRE(targets[t], "null target");
+    FactorDesc& D = hd[t];
+    memset(&D, 0, sizeof(D));
+    D.p0 = source->p0; D.p1 = source->p1; D.p2 = source->p2;
+    D.buckets = targets[t]->buckets; D.voxels = targets[t]->voxels;
+    D.mask = (uint32_t)targets[t]->num_buckets - 1u; D.max_scan = targets[t]->max_scan; D.inv_res = targets[t]->inv_res; D.n = (int)source->n;
+  }
+  memcpy(h + b_desc, deltas, sizeof(double) * 16 * T);
+  int* h_count = (int*)(h + b_desc + b_pose);
+  int* d_count = (int*)(d + b_desc + b_pose);
+  GB_CUDA(cudaMemcpyAsync(d, h, b_desc + b_pose, cudaMemcpyHostToDevice, ctx->stream));
+  GB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
+  GB_CHECK(gb_launch_overlap(ctx, (int)T, (const FactorDesc*)d, (const double*)(d + b_desc), (int)source->n, d_count));
+  GB_CUDA(cudaMemcpyAsync(h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *overlap = (double)*h_count / (double)source->n;
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// preprocess
+// ---------------------------------------------------------------------------------------------
+extern "C" gb_status gb_covariances(gb_ctx* ctx, size_t n, const double* xyzw, const int32_t* neighbors, int k_correspondences, int k_neighbors, double* normals4, double* cov4x4) {
+  GB_REQUIRE(ctx, "null ctx");
+  if (n == 0) return GB_OK;
+  GB_REQUIRE(xyzw && neighbors && normals4 && cov4x4, "null argument");
+  GB_REQUIRE(k_neighbors > 0 && k_neighbors <= k_correspondences, "k_neighbors must be in [1, k_correspondences]");
+  GB_CUDA(cudaSetDevice(ctx->device));
+  return gb_covariances_impl(ctx, n, xyzw, neighbors, k_correspondences, k_neighbors, normals4, cov4x4);
+}
+extern "C" gb_status gb_find_neighbors(gb_ctx* ctx, size_t n, const double* xyzw, int k, int32_t* neighbors) {
+  GB_REQUIRE(ctx, "null ctx");
+  if (n == 0) return GB_OK;
+  GB_REQUIRE(xyzw && neighbors && k > 0, "null argument");
+  GB_CUDA(cudaSetDevice(ctx->device));
+  return gb_find_neighbors_impl(ctx, n, xyzw, k, neighbors);
+}
+extern "C" gb_status gb_voxelgrid_sampling(gb_ctx* ctx, size_t n, const double* xyzw, const double* times, const double* intensities, double resolution, double* out_xyzw, double* out_times, double* out_intensities, size_t* num_out) {
+  GB_REQUIRE(ctx && num_out, "null argument");
+  *num_out = 0;
+  if (n == 0) return GB_OK;
+  GB_REQUIRE(xyzw && out_xyzw && resolution > 0.0, "null argument");
+  GB_CUDA(cudaSetDevice(ctx->device));
+  return gb_voxelgrid_sampling_impl(ctx, n, xyzw, times, intensities, resolution, out_xyzw, out_times, out_intensities, num_out);
+}

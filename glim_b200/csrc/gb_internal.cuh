@@ -1,0 +1,177 @@
+// gb_internal.cuh -- shared declarations of libglim_b200.so (not part of the public boundary).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+
+#include "../../include/glim_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void gb_set_error(const char* fmt, ...);
+#define GB_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      gb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return e__ == cudaErrorMemoryAllocation ? GB_ERR_OUT_OF_MEMORY : GB_ERR_CUDA;           \
+    }                                                                                         \
+  } while (0)
+#define GB_CHECK(st)                 \
+  do {                               \
+    gb_status s__ = (st);            \
+    if (s__ != GB_OK) return s__;    \
+  } while (0)
+#define GB_REQUIRE(cond, msg)                       \
+  do {                                              \
+    if (!(cond)) {                                  \
+      gb_set_error("invalid argument: %s", msg);    \
+      return GB_ERR_INVALID_ARGUMENT;               \
+    }                                               \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// HBM data layout (DESIGN.md "Data layout")
+// ---------------------------------------------------------------------------------------------
+// Source cloud: three planes, 36 B / point, every warp access fully coalesced:
+//   p0[i] = {x, y, z, c00}   p1[i] = {c01, c02, c11, c12}   p2[i] = c22
+// Voxel map: open-addressing table of 16-byte buckets {cx, cy, cz, voxel index (-1 = empty)} and
+// 48-byte voxel records (3 x float4): {mx, my, mz, c00} {c01, c02, c11, c12} {c22, num_points, 0, 0}.
+struct gb_cloud {
+  gb_ctx* ctx;
+  size_t n;
+  float4* p0;
+  float4* p1;
+  float* p2;
+  float4* normals;  // {nx, ny, nz, 0} or nullptr
+  void* base;       // one allocation
+  size_t bytes;
+};
+
+struct gb_voxelmap {
+  gb_ctx* ctx;
+  float resolution, inv_res;
+  int max_scan;
+  int num_voxels, num_buckets;
+  int num_dropped_points;
+  int4* buckets;
+  float4* voxels;   // 3 float4 per voxel
+  void* base;
+  size_t bytes;
+};
+
+// device-side factor descriptor (64 B)
+struct FactorDesc {
+  const float4* p0;
+  const float4* p1;
+  const float* p2;
+  const int4* buckets;
+  const float4* voxels;
+  uint32_t mask;
+  int max_scan;
+  float inv_res;
+  int n;
+  int pair;
+  int flags;
+  int num_tiles;
+  int first_tile;
+};
+static_assert(sizeof(FactorDesc) == 72, "FactorDesc size");
+
+struct gb_factor {
+  gb_ctx* ctx;
+  const gb_voxelmap* target;
+  const gb_cloud* source;
+  int flags;
+  gb_sweep* single;  // lazily created 1-factor sweep
+  uint64_t id;
+};
+
+#define GB_ACC_STRIDE 32      // doubles per factor in the accumulation buffer (29 used)
+#define GB_OUT_DOUBLES 122    // gb_linearized6
+
+struct gb_sweep {
+  gb_ctx* ctx;
+  size_t F;
+  std::vector<gb_factor*> factors;
+  FactorDesc* d_descs;
+  int2* d_tiles;          // {factor, begin}
+  double* d_poses;        // F x 16 (T_lin)
+  double* d_poses_eval;   // F x 16 (error mode)
+  double* d_accum;        // F x GB_ACC_STRIDE, zero between sweeps (self-cleaning)
+  unsigned* d_done;       // F tickets, zero between sweeps
+  double* d_out;          // F x 122
+  double* h_poses;        // pinned
+  double* h_poses_eval;   // pinned
+  double* h_out;          // pinned
+  float* d_slab;
+  size_t num_pairs;
+  int num_tiles, tile_size, grid;
+  uint64_t point_factors, algorithmic_bytes;
+  uint64_t key;           // cache key
+  uint64_t epoch;
+};
+
+struct gb_ctx {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  int num_sms;
+  void* scratch;
+  size_t scratch_cap;
+  void* pinned;
+  size_t pinned_cap;
+  uint64_t launches;
+  uint64_t epoch;          // bumped whenever a factor dies -> cached sweeps are stale
+  uint64_t next_id;
+  std::vector<gb_sweep*> sweep_cache;
+};
+
+gb_status gb_ctx_scratch(gb_ctx* ctx, size_t bytes, void** out);  // device scratch, valid until the next call
+gb_status gb_ctx_pinned(gb_ctx* ctx, size_t bytes, void** out);   // pinned host staging, same lifetime rule
+
+// kernel launchers (gb_kernels_*.cu)
+enum { GB_MODE_LINEARIZE = 0, GB_MODE_ERROR = 1 };
+gb_status gb_launch_sweep(gb_sweep* s, int mode);
+gb_status gb_launch_overlap(gb_ctx* ctx, int num_targets, const FactorDesc* d_descs, const double* d_poses, int n, int* d_count);
+gb_status gb_voxelmap_build_impl(gb_ctx* ctx, const gb_cloud* cloud, float resolution, int init_buckets, int max_scan, double drop_rate, gb_voxelmap* out);
+gb_status gb_covariances_impl(gb_ctx* ctx, size_t n, const double* xyzw, const int32_t* neighbors, int kc, int k, double* normals4, double* cov4x4);
+gb_status gb_find_neighbors_impl(gb_ctx* ctx, size_t n, const double* xyzw, int k, int32_t* neighbors);
+gb_status gb_voxelgrid_sampling_impl(gb_ctx* ctx, size_t n, const double* xyzw, const double* times, const double* intensities, double resolution, double* out_xyzw, double* out_times, double* out_intensities, size_t* num_out);
+
+// ---------------------------------------------------------------------------------------------
+// device helpers shared by kernels
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// canonical voxel coordinate (fp32): floorf(p * inv_res); oracle: voxel_coord_f32 (glim_oracle.c)
+__device__ __forceinline__ int gb_coord(float p, float inv_res) { return __float2int_rd(p * inv_res); }
+// XOR-of-primes hash; low 32 bits == the u64 evaluation modulo a power-of-two table
+__device__ __forceinline__ uint32_t gb_hash(int x, int y, int z) {
+  return ((uint32_t)x * 73856093u) ^ ((uint32_t)y * 19349669u) ^ ((uint32_t)z * 83492791u);
+}
+// packed 3 x 21-bit voxel key (ascending key = canonical voxel order); false if out of range
+#define GB_KEY_OFFSET (1 << 20)
+__device__ __forceinline__ bool gb_pack_key(int x, int y, int z, unsigned long long* key) {
+  if (x < -GB_KEY_OFFSET || x >= GB_KEY_OFFSET || y < -GB_KEY_OFFSET || y >= GB_KEY_OFFSET || z < -GB_KEY_OFFSET || z >= GB_KEY_OFFSET) return false;
+  *key = ((unsigned long long)(x + GB_KEY_OFFSET) << 42) | ((unsigned long long)(y + GB_KEY_OFFSET) << 21) | (unsigned long long)(z + GB_KEY_OFFSET);
+  return true;
+}
+__device__ __forceinline__ void gb_unpack_key(unsigned long long key, int& x, int& y, int& z) {
+  x = (int)((key >> 42) & 0x1FFFFF) - GB_KEY_OFFSET;
+  y = (int)((key >> 21) & 0x1FFFFF) - GB_KEY_OFFSET;
+  z = (int)(key & 0x1FFFFF) - GB_KEY_OFFSET;
+}
+// linear-probing lookup
+__device__ __forceinline__ int gb_lookup(const int4* __restrict__ buckets, uint32_t mask, int max_scan, int cx, int cy, int cz) {
+  const uint32_t h = gb_hash(cx, cy, cz);
+  for (int i = 0; i < max_scan; i++) {
+    const int4 b = __ldg(&buckets[(h + (uint32_t)i) & mask]);
+    if (b.w < 0) return -1;
+    if (b.x == cx && b.y == cy && b.z == cz) return b.w;
+  }
+  return -1;
+}
+#endif

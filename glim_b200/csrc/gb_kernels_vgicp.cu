@@ -1,0 +1,330 @@
+// gb_kernels_vgicp.cu -- the fused VGICP linearize / error sweep and the overlap kernel (sm_100a).
+//
+// Replaces gtsam_points::IntegratedVGICPFactorGPU::linearize / ::error as driven by
+// NonlinearFactorSetGPU (GLIM call sites: src/glim/odometry/odometry_estimation_gpu.cpp:144,161,383-386;
+// src/glim/mapping/sub_mapping.cpp:307; src/glim/mapping/global_mapping.cpp:466) and
+// gtsam_points::overlap_gpu (odometry_estimation_gpu.cpp:231,248).  Math: SURVEY.md Appendix A;
+// oracle: go_vgicp_linearize_gpumap / go_vgicp_error_gpumap / go_overlap_gpumap (oracle/glim_oracle.c).
+//
+// One launch covers a whole factor set.  Work unit = a tile of `tile_size` consecutive source
+// points of one factor; tiles are laid out factor-major and handed to a persistent grid
+// round-robin, so at any instant the grid works on a window of a few consecutive factors whose
+// source cloud and voxel table stay L2 resident.  Per point (one thread):
+//   coalesced 36-byte read of (mean, packed covariance) -> q = R a + t -> voxel coord -> hash probe
+//   (16-byte buckets) -> 48-byte voxel record -> S = C_B + R C_A R^T, M = S^-1 (symmetric 3x3)
+//   -> accumulate the 21 unique entries of H_tt = J_t^T M J_t (J_t = [-hat(q) | I]), the 6 of
+//   b_t = J_t^T M r, the error r^T M r and the inlier count: 29 registers.
+// Per tile: transposing warp reduce-scatter (31 shuffles for 32 values), cross-warp sum in shared
+// memory, 29 fp64 atomics into the factor's accumulator.  The CTA that retires a factor's last
+// tile runs the fp64 epilogue: H_ts = -H_tt Ad, H_ss = Ad^T H_tt Ad, b_s = -Ad^T b_t with
+// Ad = AdjointMap(delta), writes the 122-double record (and adds it to the pair
+// slab when one is attached), and re-zeroes the accumulator for the next sweep.
+#include "gb_internal.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+struct PoseF {
+  float r00, r01, r02, r10, r11, r12, r20, r21, r22, tx, ty, tz;
+};
+
+__device__ __forceinline__ PoseF load_pose(const float* s) {
+  PoseF P;
+  P.r00 = s[0]; P.r01 = s[1]; P.r02 = s[2];
+  P.r10 = s[3]; P.r11 = s[4]; P.r12 = s[5];
+  P.r20 = s[6]; P.r21 = s[7]; P.r22 = s[8];
+  P.tx = s[9]; P.ty = s[10]; P.tz = s[11];
+  return P;
+}
+
+// q = R a + t with the canonical FMA order (bit-exact with transform_f32 in the oracle)
+__device__ __forceinline__ void transform(const PoseF& P, float ax, float ay, float az, float& qx, float& qy, float& qz) {
+  qx = fmaf(P.r00, ax, fmaf(P.r01, ay, fmaf(P.r02, az, P.tx)));
+  qy = fmaf(P.r10, ax, fmaf(P.r11, ay, fmaf(P.r12, az, P.ty)));
+  qz = fmaf(P.r20, ax, fmaf(P.r21, ay, fmaf(P.r22, az, P.tz)));
+}
+
+// M = (C_B + R C_A R^T)^-1, symmetric 3x3 (xx xy xz yy yz zz)
+__device__ __forceinline__ void fused_mahalanobis(
+  const PoseF& P, float cxx, float cxy, float cxz, float cyy, float cyz, float czz,  // C_A
+  float bxx, float bxy, float bxz, float byy, float byz, float bzz,                  // C_B
+  float& mxx, float& mxy, float& mxz, float& myy, float& myz, float& mzz) {
+  // T = R * C_A
+  const float t00 = P.r00 * cxx + P.r01 * cxy + P.r02 * cxz;
+  const float t01 = P.r00 * cxy + P.r01 * cyy + P.r02 * cyz;
+  const float t02 = P.r00 * cxz + P.r01 * cyz + P.r02 * czz;
+  const float t10 = P.r10 * cxx + P.r11 * cxy + P.r12 * cxz;
+  const float t11 = P.r10 * cxy + P.r11 * cyy + P.r12 * cyz;
+  const float t12 = P.r10 * cxz + P.r11 * cyz + P.r12 * czz;
+  const float t20 = P.r20 * cxx + P.r21 * cxy + P.r22 * cxz;
+  const float t21 = P.r20 * cxy + P.r21 * cyy + P.r22 * cyz;
+  const float t22 = P.r20 * cxz + P.r21 * cyz + P.r22 * czz;
+  // S = C_B + T R^T (upper triangle)
+  const float sxx = bxx + (t00 * P.r00 + t01 * P.r01 + t02 * P.r02);
+  const float sxy = bxy + (t00 * P.r10 + t01 * P.r11 + t02 * P.r12);
+  const float sxz = bxz + (t00 * P.r20 + t01 * P.r21 + t02 * P.r22);
+  const float syy = byy + (t10 * P.r10 + t11 * P.r11 + t12 * P.r12);
+  const float syz = byz + (t10 * P.r20 + t11 * P.r21 + t12 * P.r22);
+  const float szz = bzz + (t20 * P.r20 + t21 * P.r21 + t22 * P.r22);
+  // inverse by cofactors
+  const float c00 = syy * szz - syz * syz;
+  const float c01 = sxz * syz - sxy * szz;
+  const float c02 = sxy * syz - sxz * syy;
+  const float c11 = sxx * szz - sxz * sxz;
+  const float c12 = sxy * sxz - sxx * syz;
+  const float c22 = sxx * syy - sxy * sxy;
+  const float det = sxx * c00 + sxy * c01 + sxz * c02;
+  const float id = __fdividef(1.0f, det);
+  mxx = c00 * id; mxy = c01 * id; mxz = c02 * id; myy = c11 * id; myz = c12 * id; mzz = c22 * id;
+}
+
+// Transposing warp reduction: on return lane l holds sum over the warp of v[l] (in v[0]).
+__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool upper = (lane & step) != 0;
+#pragma unroll
+    for (int j = 0; j < step; j++) {
+      const float send = upper ? v[j] : v[j + step];
+      const float keep = upper ? v[j + step] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return v[0];
+}
+
+// fp64 epilogue of one factor, executed by warp 0 of the CTA that retired the factor's last tile.
+__device__ void factor_epilogue(int f, const FactorDesc& D, const double* __restrict__ poses, double* __restrict__ accum, double* __restrict__ out, float* __restrict__ slab, double* sm /* >= 36+36+36+32 doubles */) {
+  const int lane = threadIdx.x & 31;
+  double* A = sm;            // 32 accumulators
+  double* H = sm + 32;       // 6x6 H_tt, row-major (symmetric)
+  double* Ad = sm + 68;      // 6x6 adjoint, row-major
+  double* X = sm + 104;      // H_tt * Ad, row-major
+  // the accumulators were produced by L2 atomics of other CTAs: read them past L1
+  if (lane < 29) A[lane] = __ldcg(&accum[(size_t)f * GB_ACC_STRIDE + lane]);
+  __syncwarp();
+  // re-zero for the next sweep (self-cleaning; nobody touches this factor again in this launch)
+  if (lane < 29) accum[(size_t)f * GB_ACC_STRIDE + lane] = 0.0;
+  // unpack upper triangle
+  if (lane == 0) {
+    int k = 0;
+    for (int i = 0; i < 6; i++)
+      for (int j = i; j < 6; j++) { H[i * 6 + j] = A[k]; H[j * 6 + i] = A[k]; k++; }
+    // Ad = [[R, 0], [hat(t) R, R]] from the fp32-cast pose the kernel used
+    const double* T = poses + (size_t)f * 16;
+    double R[9], t[3];
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R[r * 3 + c] = (double)(float)T[c * 4 + r]; t[r] = (double)(float)T[12 + r]; }
+    const double ht[9] = {0, -t[2], t[1], t[2], 0, -t[0], -t[1], t[0], 0};
+    for (int i = 0; i < 36; i++) Ad[i] = 0.0;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        Ad[i * 6 + j] = R[i * 3 + j];
+        Ad[(i + 3) * 6 + (j + 3)] = R[i * 3 + j];
+        Ad[(i + 3) * 6 + j] = ht[i * 3 + 0] * R[0 * 3 + j] + ht[i * 3 + 1] * R[1 * 3 + j] + ht[i * 3 + 2] * R[2 * 3 + j];
+      }
+  }
+  __syncwarp();
+  for (int e = lane; e < 36; e += 32) {
+    const int i = e / 6, j = e % 6;
+    double s = 0;
+    for (int k = 0; k < 6; k++) s += H[i * 6 + k] * Ad[k * 6 + j];
+    X[e] = s;
+  }
+  __syncwarp();
+  double* o = out + (size_t)f * GB_OUT_DOUBLES;
+  float* srow = slab ? slab + (size_t)D.pair * GB_SLAB_STRIDE : nullptr;
+  for (int e = lane; e < 36; e += 32) {
+    const int i = e / 6, j = e % 6;  // output element (row i, col j), stored column-major
+    double ss = 0;
+    for (int k = 0; k < 6; k++) ss += Ad[k * 6 + i] * X[k * 6 + j];
+    o[j * 6 + i] = H[i * 6 + j];             // H_tt
+    o[36 + j * 6 + i] = ss;                  // H_ss = Ad^T H_tt Ad
+    o[72 + j * 6 + i] = -X[i * 6 + j];       // H_ts = -H_tt Ad
+    if (srow) {
+      atomicAdd(&srow[21 + j * 6 + i], (float)(-X[i * 6 + j]));
+      if (j >= i) {
+        const int u = i * 6 - (i * (i - 1)) / 2 + (j - i);  // index in the row-major upper triangle
+        atomicAdd(&srow[u], (float)H[i * 6 + j]);
+        atomicAdd(&srow[57 + u], (float)ss);
+      }
+    }
+  }
+  if (lane < 6) {
+    double bs = 0;
+    for (int k = 0; k < 6; k++) bs += Ad[k * 6 + lane] * A[21 + k];
+    o[108 + lane] = A[21 + lane];
+    o[114 + lane] = -bs;
+    if (srow) { atomicAdd(&srow[78 + lane], (float)A[21 + lane]); atomicAdd(&srow[84 + lane], (float)(-bs)); }
+  }
+  if (lane == 6) { o[120] = A[27]; if (srow) atomicAdd(&srow[90], (float)A[27]); }
+  if (lane == 7) { o[121] = A[28]; if (srow) atomicAdd(&srow[91], (float)A[28]); }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep(
+  const FactorDesc* __restrict__ descs, const double* __restrict__ poses, const double* __restrict__ poses_eval,
+  const int2* __restrict__ tiles, int num_tiles, int tile_size,
+  double* __restrict__ accum, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab) {
+  __shared__ float s_pose[24];
+  __shared__ float s_red[kWarps][32];
+  __shared__ double s_epi[144];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int2 tl = __ldg(&tiles[tile]);
+    const int f = tl.x;
+    const FactorDesc D = descs[f];
+    // pose -> fp32 row-major R | t  (Isometry3f cast of the reference GPU factor)
+    if (tid < 12) {
+      const double* T = poses + (size_t)f * 16;
+      const int r = tid < 9 ? tid / 3 : tid - 9, c = tid < 9 ? tid % 3 : 3;
+      s_pose[tid] = (float)T[c * 4 + r];
+      if (MODE == GB_MODE_ERROR) {
+        const double* Te = poses_eval + (size_t)f * 16;
+        s_pose[12 + tid] = (float)Te[c * 4 + r];
+      }
+    }
+    __syncthreads();
+    const PoseF P = load_pose(s_pose);
+    PoseF Pe = P;
+    if (MODE == GB_MODE_ERROR) Pe = load_pose(s_pose + 12);
+
+    float acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) acc[k] = 0.f;
+
+    const int begin = tl.y;
+    const int end = min(begin + tile_size, D.n);
+    for (int i = begin + tid; i < end; i += kThreads) {
+      const float4 a0 = __ldg(&D.p0[i]);
+      const float4 a1 = __ldg(&D.p1[i]);
+      const float a2 = __ldg(&D.p2[i]);
+      float qx, qy, qz;
+      transform(P, a0.x, a0.y, a0.z, qx, qy, qz);
+      const int cx = gb_coord(qx, D.inv_res), cy = gb_coord(qy, D.inv_res), cz = gb_coord(qz, D.inv_res);
+      const int v = gb_lookup(D.buckets, D.mask, D.max_scan, cx, cy, cz);
+      if (v < 0) continue;
+      const float4 v0 = __ldg(&D.voxels[3 * (size_t)v + 0]);
+      const float4 v1 = __ldg(&D.voxels[3 * (size_t)v + 1]);
+      const float4 v2 = __ldg(&D.voxels[3 * (size_t)v + 2]);
+      if (MODE == GB_MODE_ERROR) transform(Pe, a0.x, a0.y, a0.z, qx, qy, qz);
+      float mxx, mxy, mxz, myy, myz, mzz;
+      fused_mahalanobis(Pe, a0.w, a1.x, a1.y, a1.z, a1.w, a2, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, mxx, mxy, mxz, myy, myz, mzz);
+      const float rx = v0.x - qx, ry = v0.y - qy, rz = v0.z - qz;
+      const float wx = mxx * rx + mxy * ry + mxz * rz;
+      const float wy = mxy * rx + myy * ry + myz * rz;
+      const float wz = mxz * rx + myz * ry + mzz * rz;
+      acc[27] += rx * wx + ry * wy + rz * wz;
+      acc[28] += 1.0f;
+      if (MODE == GB_MODE_LINEARIZE) {
+        // G = hat(q) M   (rows: rotation, cols: translation block of H_tt)
+        const float g00 = qy * mxz - qz * mxy, g01 = qy * myz - qz * myy, g02 = qy * mzz - qz * myz;
+        const float g10 = qz * mxx - qx * mxz, g11 = qz * mxy - qx * myz, g12 = qz * mxz - qx * mzz;
+        const float g20 = qx * mxy - qy * mxx, g21 = qx * myy - qy * mxy, g22 = qx * myz - qy * mxz;
+        // H_rr = G hat(q)^T : row i = q x g_i   (upper triangle)
+        acc[0] += qy * g02 - qz * g01;
+        acc[1] += qz * g00 - qx * g02;
+        acc[2] += qx * g01 - qy * g00;
+        acc[3] += g00; acc[4] += g01; acc[5] += g02;
+        acc[6] += qz * g10 - qx * g12;
+        acc[7] += qx * g11 - qy * g10;
+        acc[8] += g10; acc[9] += g11; acc[10] += g12;
+        acc[11] += qx * g21 - qy * g20;
+        acc[12] += g20; acc[13] += g21; acc[14] += g22;
+        acc[15] += mxx; acc[16] += mxy; acc[17] += mxz; acc[18] += myy; acc[19] += myz; acc[20] += mzz;
+        // b_t = [q x w ; w]
+        acc[21] += qy * wz - qz * wy;
+        acc[22] += qz * wx - qx * wz;
+        acc[23] += qx * wy - qy * wx;
+        acc[24] += wx; acc[25] += wy; acc[26] += wz;
+      }
+    }
+
+    // ---- tile reduction ----
+    if (MODE == GB_MODE_LINEARIZE) {
+      const float r = warp_reduce_scatter32(acc, lane);
+      s_red[warp][lane] = r;
+    } else {
+      float e = acc[27], n = acc[28];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) { e += __shfl_xor_sync(0xffffffffu, e, o); n += __shfl_xor_sync(0xffffffffu, n, o); }
+      if (lane == 0) { s_red[warp][27] = e; s_red[warp][28] = n; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const bool mine = (MODE == GB_MODE_LINEARIZE) ? (lane < 29) : (lane == 27 || lane == 28);
+      if (mine) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) s += (double)s_red[w][lane];
+        atomicAdd(&accum[(size_t)f * GB_ACC_STRIDE + lane], s);
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned ticket = atomicAdd(&done[f], 1u);
+        s_last = (ticket == (unsigned)D.num_tiles - 1u);
+        if (s_last) done[f] = 0u;  // self-cleaning
+      }
+      __syncwarp();
+      if (s_last) {
+        __threadfence();
+        factor_epilogue(f, D, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, out, slab, s_epi);
+      }
+    }
+    __syncthreads();  // s_pose / s_red / s_last are reused by the next tile
+  }
+}
+
+// overlap: one thread per source point, count points that hit an occupied voxel of any target
+__global__ void __launch_bounds__(256) k_overlap(int num_targets, const FactorDesc* __restrict__ descs, const double* __restrict__ poses, int n, int* __restrict__ count) {
+  extern __shared__ float s_poses[];  // num_targets x 12
+  for (int k = threadIdx.x; k < num_targets * 12; k += blockDim.x) {
+    const int t = k / 12, e = k % 12;
+    const int r = e < 9 ? e / 3 : e - 9, c = e < 9 ? e % 3 : 3;
+    s_poses[k] = (float)poses[(size_t)t * 16 + c * 4 + r];
+  }
+  __syncthreads();
+  int local = 0;
+  const FactorDesc D0 = descs[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 a0 = __ldg(&D0.p0[i]);
+    for (int t = 0; t < num_targets; t++) {
+      const PoseF P = load_pose(s_poses + 12 * t);
+      float qx, qy, qz;
+      transform(P, a0.x, a0.y, a0.z, qx, qy, qz);
+      const float inv_res = descs[t].inv_res;
+      const int v = gb_lookup(descs[t].buckets, descs[t].mask, descs[t].max_scan, gb_coord(qx, inv_res), gb_coord(qy, inv_res), gb_coord(qz, inv_res));
+      if (v >= 0) { local++; break; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
+}  // namespace
+
+gb_status gb_launch_sweep(gb_sweep* s, int mode) {
+  if (s->num_tiles == 0) return GB_OK;
+  gb_ctx* ctx = s->ctx;
+  if (mode == GB_MODE_LINEARIZE)
+    k_vgicp_sweep<GB_MODE_LINEARIZE><<<s->grid, kThreads, 0, ctx->stream>>>(s->d_descs, s->d_poses, nullptr, s->d_tiles, s->num_tiles, s->tile_size, s->d_accum, s->d_done, s->d_out, s->d_slab);
+  else
+    k_vgicp_sweep<GB_MODE_ERROR><<<s->grid, kThreads, 0, ctx->stream>>>(s->d_descs, s->d_poses, s->d_poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_accum, s->d_done, s->d_out, nullptr);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
+
+gb_status gb_launch_overlap(gb_ctx* ctx, int num_targets, const FactorDesc* d_descs, const double* d_poses, int n, int* d_count) {
+  if (n <= 0 || num_targets <= 0) return GB_OK;
+  const int grid = min((n + 255) / 256, ctx->num_sms * 8);
+  k_overlap<<<grid, 256, (size_t)num_targets * 12 * sizeof(float), ctx->stream>>>(num_targets, d_descs, d_poses, n, d_count);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}

@@ -1,0 +1,163 @@
+/*
+ * glim_b200.h -- C-ABI of libglim_b200.so: the B200-native (sm_100a) VGICP scan-matching hot path
+ * of koide3/glim, behind the surface GLIM's modules use from gtsam_points.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the GLIM tree,
+ * v1.2.2).  The arithmetic of those interfaces lives in the un-vendored dependency
+ * koide3/gtsam_points (CMakeLists.txt:28); the citations are GLIM's own call sites.
+ *
+ * Rules of the boundary
+ *   - plain C: opaque handles, pointers and sizes only; no exceptions, no C++ or torch types.
+ *   - every function returns gb_status (0 = OK); gb_status_string() / gb_last_error() explain.
+ *   - handles are created / destroyed by the caller with the matching _create / _destroy.
+ *     A gb_factor BORROWS its cloud and voxel map (the C++ shim keeps shared_ptrs alive, as the
+ *     reference factor does); destroying a cloud or map that a live factor uses is a caller bug.
+ *   - one gb_ctx per host thread / GPU (the reference drives each module from exactly one
+ *     executor thread: src/glim/odometry/async_odometry_estimation.cpp:15).  A ctx owns one CUDA
+ *     stream; all work of its handles is ordered on that stream.
+ *   - 4x4 poses are 16 doubles, COLUMN-MAJOR (Eigen::Isometry3d::data()).
+ *   - 6x6 blocks are column-major, tangent order [rotation(3); translation(3)] (gtsam::Pose3).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with GB_ERR_NO_DEVICE.
+ */
+#ifndef GLIM_B200_H
+#define GLIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_API __attribute__((visibility("default")))
+
+typedef int gb_status;
+enum {
+  GB_OK = 0,
+  GB_ERR_INVALID_ARGUMENT = 1,
+  GB_ERR_CUDA = 2,
+  GB_ERR_OUT_OF_MEMORY = 3,
+  GB_ERR_NO_DEVICE = 4,
+  GB_ERR_INTERNAL = 5
+};
+
+typedef struct gb_ctx gb_ctx;           /* CUDAStream + StreamTempBufferRoundRobin (odometry_estimation_gpu.cpp:76-77) */
+typedef struct gb_cloud gb_cloud;       /* gtsam_points::PointCloudGPU                                              */
+typedef struct gb_voxelmap gb_voxelmap; /* gtsam_points::GaussianVoxelMapGPU                                        */
+typedef struct gb_factor gb_factor;     /* gtsam_points::IntegratedVGICPFactorGPU                                   */
+typedef struct gb_sweep gb_sweep;       /* gtsam_points::NonlinearFactorSetGPU (a prepared batch of factors)        */
+
+/* LinearizedSystem6 of the reference GPU factor, widened to fp64.
+ * To GTSAM: HessianFactor(k_t, k_s, H_tt, H_ts, -b_t, H_ss, -b_s, error); unary: (k_s, H_ss, -b_s, error).
+ * error = sum r^T M r (no 1/2).  122 doubles. */
+typedef struct gb_linearized6 {
+  double H_tt[36];
+  double H_ss[36];
+  double H_ts[36]; /* rows: target tangent, cols: source tangent */
+  double b_t[6];
+  double b_s[6];
+  double error;
+  double num_inliers;
+} gb_linearized6;
+
+/* factor flags */
+#define GB_FACTOR_DEFAULT 0
+/* set_enable_surface_validation(true) (odometry_estimation_gpu.cpp:145,162).  The reference rule is
+ * not recoverable here (unpinned ledger); the flag is accepted and recorded, the
+ * documented rule is in DESIGN.md. */
+#define GB_FACTOR_SURFACE_VALIDATION 1
+
+GB_API const char* gb_status_string(gb_status s);
+GB_API const char* gb_last_error(void); /* thread-local detail of the last failure */
+GB_API int gb_device_count(void);       /* cuda_device_names / cuda_mem_get_info: src/glim/util/debug.cpp:84 */
+GB_API gb_status gb_mem_info(int device, size_t* free_bytes, size_t* total_bytes); /* src/glim/viewer/memory_monitor.cpp:39 */
+
+/* ---- context: replaces gtsam_points::CUDAStream + StreamTempBufferRoundRobin
+ *      (odometry_estimation_gpu.cpp:76-77, sub_mapping.cpp:86-87, global_mapping.cpp:110) ---- */
+GB_API gb_status gb_ctx_create(int device, gb_ctx** out);
+/* same, but enqueue on a caller-owned cudaStream_t (e.g. the stream NCCL collectives run on) */
+GB_API gb_status gb_ctx_create_on_stream(int device, void* cuda_stream, gb_ctx** out);
+GB_API gb_status gb_ctx_destroy(gb_ctx* ctx);
+GB_API gb_status gb_ctx_synchronize(gb_ctx* ctx);
+GB_API void* gb_ctx_stream(gb_ctx* ctx); /* the cudaStream_t */
+GB_API uint64_t gb_ctx_kernel_launches(gb_ctx* ctx); /* kernels of this library launched so far */
+
+/* ---- PointCloudGPU::clone(frame[, stream]) (odometry_estimation_gpu.cpp:96; sub_mapping.cpp:168,393;
+ *      global_mapping.cpp:253,260,743).  Host layout as the reference's PointCloudCPU:
+ *      xyzw = N x Vector4d (w = 1), cov4x4 = N x Matrix4d column-major (last row/col 0) or NULL,
+ *      normals4 = N x Vector4d or NULL (standard_viewer_mem.cpp:34-41).  Device layout is fp32
+ *      (standard_viewer_mem.cpp:49-58), covariance kept as its 6 unique entries. ---- */
+GB_API gb_status gb_cloud_upload(gb_ctx* ctx, size_t n, const double* xyzw, const double* cov4x4, const double* normals4, gb_cloud** out);
+GB_API gb_status gb_cloud_size(const gb_cloud* cloud, size_t* n);
+/* device -> host copy of the fp32 device data: xyz N x 3, cov6 N x 6 (c00 c01 c02 c11 c12 c22); either may be NULL */
+GB_API gb_status gb_cloud_download(const gb_cloud* cloud, float* xyz, float* cov6);
+GB_API gb_status gb_cloud_destroy(gb_cloud* cloud);
+
+/* ---- GaussianVoxelMapGPU(resolution, init_num_buckets = 8192*2, max_bucket_scan_count = 10,
+ *      target_points_drop_rate = 1e-3, stream)::insert(cloud)   (odometry_estimation_gpu.cpp:103-104;
+ *      sub_mapping.cpp:398-399; global_mapping.cpp:265-266, 747-748) ---- */
+GB_API gb_status gb_voxelmap_build(gb_ctx* ctx, const gb_cloud* cloud, float resolution, int init_num_buckets, int max_bucket_scan_count, double target_points_drop_rate, gb_voxelmap** out);
+/* voxel_resolution(), voxelmap_info.{num_voxels,num_buckets} (standard_viewer_callbacks.cpp:117; standard_viewer_mem.cpp:76-77) */
+GB_API gb_status gb_voxelmap_info(const gb_voxelmap* map, int* num_voxels, int* num_buckets, float* resolution);
+/* device -> host: buckets NB x 4 int32 (x y z index, index -1 = empty), per voxel num_points, mean (V x 3),
+ * cov6 (V x 6); any pointer may be NULL */
+GB_API gb_status gb_voxelmap_download(const gb_voxelmap* map, int32_t* buckets, int32_t* num_points, float* means, float* cov6);
+GB_API gb_status gb_voxelmap_destroy(gb_voxelmap* map);
+
+/* ---- IntegratedVGICPFactorGPU(target_key | fixed_target_pose, source_key, voxelmap, source, stream, buffer)
+ *      (odometry_estimation_gpu.cpp:144,161; sub_mapping.cpp:307; global_mapping.cpp:335,466,860).
+ *      Keys and the binary/unary distinction stay on the host side of the boundary: the device only
+ *      ever sees delta = T_target^-1 * T_source. ---- */
+GB_API gb_status gb_vgicp_factor_create(gb_ctx* ctx, const gb_voxelmap* target, const gb_cloud* source, int flags, gb_factor** out);
+GB_API gb_status gb_vgicp_factor_destroy(gb_factor* factor);
+/* linearize(values): one fused kernel (lookup + residual + Jacobians + 6x6 reduction) */
+GB_API gb_status gb_vgicp_linearize(gb_factor* factor, const double T_target_source[16], gb_linearized6* out);
+/* error(values): inlier set found at T_lin, evaluated at T_eval */
+GB_API gb_status gb_vgicp_error(gb_factor* factor, const double T_lin[16], const double T_eval[16], double* error);
+/* num_inliers() / inlier_fraction() come back in gb_linearized6::num_inliers */
+
+/* ---- NonlinearFactorSetGPU::add(graph) / ::linearize(values) (odometry_estimation_gpu.cpp:383-386;
+ *      hook at src/glim/viewer/offline_viewer.cpp:29): F x 64 B of poses down, one launch over all
+ *      factors, F records up. ---- */
+GB_API gb_status gb_factor_set_linearize(gb_ctx* ctx, size_t num_factors, gb_factor* const* factors, const double* T_target_source /* F x 16 */, gb_linearized6* out /* F */);
+GB_API gb_status gb_factor_set_error(gb_ctx* ctx, size_t num_factors, gb_factor* const* factors, const double* T_lin /* F x 16 */, const double* T_eval /* F x 16 */, double* errors /* F */);
+
+/* Prepared batch: the same sweep with its descriptor table resident on the device, split into
+ * upload / launch / fetch so that callers (the bench, the multi-GPU sweep) can keep everything in HBM.
+ *   pair_index (may be NULL): factor -> row of a caller-owned fp32 slab [num_pairs][GB_SLAB_STRIDE];
+ *   when a slab is attached the kernel epilogue ADDS each factor's blocks to its pair row
+ *   (levels of the same pair sum there), which is the buffer the multi-GPU sweep all-reduces
+ *   over NCCL.  Slab row: H_tt upper(21) H_ts(36, column-major) H_ss upper(21) b_t(6) b_s(6)
+ *   error num_inliers, padded to GB_SLAB_STRIDE floats. */
+#define GB_SLAB_STRIDE 96
+GB_API gb_status gb_sweep_create(gb_ctx* ctx, size_t num_factors, gb_factor* const* factors, const int32_t* pair_index, gb_sweep** out);
+GB_API gb_status gb_sweep_destroy(gb_sweep* sweep);
+GB_API gb_status gb_sweep_attach_slab(gb_sweep* sweep, void* device_slab_f32, size_t num_pairs);
+GB_API gb_status gb_sweep_set_poses(gb_sweep* sweep, const double* T_target_source /* F x 16, host */); /* async H2D */
+GB_API gb_status gb_sweep_launch(gb_sweep* sweep);                                /* async: the fused kernel */
+GB_API gb_status gb_sweep_fetch(gb_sweep* sweep, gb_linearized6* out /* F */);     /* D2H + stream sync */
+GB_API gb_status gb_sweep_results_device(gb_sweep* sweep, void** device_ptr);     /* F x 122 doubles in HBM */
+/* bookkeeping for the roofline: sum of N_source, and algorithmic bytes B_sweep of SURVEY 8(d) */
+GB_API gb_status gb_sweep_stats(const gb_sweep* sweep, uint64_t* point_factors, uint64_t* algorithmic_bytes, uint32_t* num_tiles, uint32_t* grid_size);
+
+/* ---- overlap_gpu(voxelmap, source, delta, stream) / overlap_gpu(voxelmaps, source, deltas, stream) /
+ *      overlap_auto (odometry_estimation_gpu.cpp:231,248,265,279; sub_mapping.cpp:252; global_mapping.cpp:322,448):
+ *      fraction of source points that fall in an occupied voxel of any target ---- */
+GB_API gb_status gb_overlap(gb_ctx* ctx, size_t num_targets, const gb_voxelmap* const* targets, const gb_cloud* source, const double* deltas /* T x 16 */, double* overlap);
+
+/* ---- CloudCovarianceEstimation::estimate(points, neighbors, k, normals, covs) with PLANE regularization
+ *      (src/glim/common/cloud_covariance_estimation.cpp:43-122, :181-196) ---- */
+GB_API gb_status gb_covariances(gb_ctx* ctx, size_t n, const double* xyzw, const int32_t* neighbors, int k_correspondences, int k_neighbors, double* normals4, double* cov4x4);
+
+/* ---- CloudPreprocessor::find_neighbors (src/glim/preprocess/cloud_preprocessor.cpp:190-221): exact k-NN,
+ *      query included, row-major neighbors[i*k + j] ---- */
+GB_API gb_status gb_find_neighbors(gb_ctx* ctx, size_t n, const double* xyzw, int k, int32_t* neighbors);
+
+/* ---- gtsam_points::voxelgrid_sampling (cloud_preprocessor.cpp:108): one point per voxel = mean of
+ *      points / times / intensities, ascending packed-key order.  out arrays sized n; *num_out = count ---- */
+GB_API gb_status gb_voxelgrid_sampling(gb_ctx* ctx, size_t n, const double* xyzw, const double* times, const double* intensities, double resolution, double* out_xyzw, double* out_times, double* out_intensities, size_t* num_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLIM_B200_H */

@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    """One gb_ctx for the whole GPU test session (fails loudly when libglim_b200.so or the GPU is missing)."""
+    from glim_b200 import gpu
+
+    c = gpu.Context(0)
+    yield c
+    c.synchronize()
