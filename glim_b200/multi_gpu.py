@@ -1,0 +1,92 @@
+"""Sharding of a global-mapping relinearization sweep across the GPUs of one box.
+
+The reference has no multi-GPU notion; this is the B200-native addition north_star asks for.
+Every rank holds all submap clouds and voxel maps (replicated at insert time, < 1 GB); the (target, source) PAIRS of
+the factor graph are partitioned over the ranks (both voxel levels of a pair stay together, longest-processing-time
+first on the source size); each rank sweeps its factors with the fused kernel, whose epilogue adds every factor's
+blocks into its pair's row of a zeroed fp32 slab [num_pairs][GB_SLAB_STRIDE]; one all-reduce (sum) of the slab over
+NCCL / NVLink gives every rank the complete block-sparse Hessian for the host solver.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .capi import GB_SLAB_STRIDE
+
+
+def lpt_partition(weights, n_parts: int):
+    """Longest-processing-time-first: returns part index per item; deterministic (ties by index)."""
+    weights = np.asarray(weights, dtype=np.float64)
+    order = sorted(range(len(weights)), key=lambda i: (-weights[i], i))
+    load = [0.0] * n_parts
+    part = np.zeros(len(weights), dtype=np.int64)
+    for i in order:
+        p = min(range(n_parts), key=lambda k: (load[k], k))
+        part[i] = p
+        load[p] += weights[i]
+    return part
+
+
+def shard_factors(factors, source_sizes, world: int):
+    """factors: objects with .pair and .source; -> (rank per factor, rank per pair).  Pairs are kept whole."""
+    pairs = sorted({f.pair for f in factors})
+    index = {p: k for k, p in enumerate(pairs)}
+    w = np.zeros(len(pairs))
+    for f in factors:
+        w[index[f.pair]] += source_sizes[f.source]
+    pair_rank = lpt_partition(w, world)
+    return np.array([pair_rank[index[f.pair]] for f in factors], dtype=np.int64), {p: int(pair_rank[index[p]]) for p in pairs}
+
+
+def unpack_slab_row(row):
+    """fp32 slab row -> dict of 6x6 / 6 blocks (see GB_SLAB_STRIDE in include/glim_b200.h)."""
+    row = np.asarray(row, dtype=np.float64)
+    iu = np.triu_indices(6)
+
+    def sym(v):
+        M = np.zeros((6, 6))
+        M[iu] = v
+        return M + np.triu(M, 1).T
+
+    return {
+        "H_tt": sym(row[0:21]),
+        "H_ts": row[21:57].reshape(6, 6).T.copy(),
+        "H_ss": sym(row[57:78]),
+        "b_t": row[78:84].copy(),
+        "b_s": row[84:90].copy(),
+        "error": float(row[90]),
+        "num_inliers": float(row[91]),
+    }
+
+
+def pack_slab_row(rec: dict) -> np.ndarray:
+    """Inverse of unpack_slab_row for [row, col] blocks (host-side reference used by the CPU tests)."""
+    iu = np.triu_indices(6)
+    row = np.zeros(GB_SLAB_STRIDE, dtype=np.float32)
+    row[0:21] = rec["H_tt"][iu]
+    row[21:57] = rec["H_ts"].T.reshape(36)
+    row[57:78] = rec["H_ss"][iu]
+    row[78:84] = rec["b_t"]
+    row[84:90] = rec["b_s"]
+    row[90] = rec["error"]
+    row[91] = rec["num_inliers"]
+    return row
+
+
+class ShardedSweep:
+    """One rank's share of a sweep + the slab all-reduce.  `launch` is a callable that enqueues this rank's kernel
+    (adds into `slab`); on the GPU it is gpu.Sweep.launch, in the CPU (gloo) tests a host stand-in."""
+
+    def __init__(self, slab, launch, world: int):
+        self.slab = slab  # torch tensor [num_pairs, GB_SLAB_STRIDE] float32
+        self.launch = launch
+        self.world = world
+
+    def step(self):
+        import torch.distributed as dist
+
+        self.slab.zero_()
+        self.launch()
+        if self.world > 1:
+            dist.all_reduce(self.slab, op=dist.ReduceOp.SUM)
+        return self.slab

@@ -218,12 +218,62 @@ def sensor_pattern(name: str, rng: np.random.Generator | None = None, n_rays: in
     raise ValueError(name)
 
 
-def scan(scene: Scene, sensor: str, T_world_sensor: np.ndarray, rng: np.random.Generator, n_rays: int | None = None, min_range=0.5, max_range=100.0, noise=0.02):
+def _raycast_torch(scene: Scene, o: np.ndarray, d: np.ndarray, max_range: float):
+    """Same ray caster on the GPU with torch (fp64) -- only used to build synthetic bench inputs quickly."""
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    D = torch.from_numpy(np.ascontiguousarray(d)).to(dev)
+    O = torch.from_numpy(np.asarray(o, dtype=np.float64)).to(dev)
+    eps = 1e-12
+    inv = 1.0 / torch.where(D.abs() < eps, torch.full_like(D, eps), D)
+    inf = torch.full((D.shape[0],), float("inf"), dtype=torch.float64, device=dev)
+    tg = (scene.ground_z - O[2]) * inv[:, 2]
+    t_best = torch.where(tg > 1e-6, tg, inf)
+    if scene.room is not None:
+        room = torch.from_numpy(scene.room).to(dev)
+        t1 = (room[0] - O) * inv
+        t2 = (room[1] - O) * inv
+        texit = torch.maximum(t1, t2).min(dim=1).values
+        t_best = torch.minimum(t_best, torch.where(texit > 1e-6, texit, inf))
+    if len(scene.boxes):
+        ctr = 0.5 * (scene.boxes[:, 0] + scene.boxes[:, 1])
+        rad = 0.5 * np.linalg.norm(scene.boxes[:, 1] - scene.boxes[:, 0], axis=1)
+        near = scene.boxes[np.linalg.norm(ctr - o, axis=1) - rad < max_range]
+        for c0 in range(0, len(near), 32):
+            B = torch.from_numpy(near[c0 : c0 + 32]).to(dev)  # (b,2,3)
+            t1 = (B[None, :, 0, :] - O) * inv[:, None, :]
+            t2 = (B[None, :, 1, :] - O) * inv[:, None, :]
+            tn = torch.minimum(t1, t2).max(dim=2).values
+            tf = torch.maximum(t1, t2).min(dim=2).values
+            tn = torch.where((tn <= tf) & (tn > 1e-6), tn, torch.full_like(tn, float("inf")))
+            t_best = torch.minimum(t_best, tn.min(dim=1).values)
+    if len(scene.cylinders):
+        cc = scene.cylinders
+        near = cc[np.hypot(cc[:, 0] - o[0], cc[:, 1] - o[1]) - cc[:, 2] < max_range]
+        if len(near):
+            Cy = torch.from_numpy(near).to(dev)  # (c,5)
+            ox = (O[0] - Cy[:, 0])[None, :]
+            oy = (O[1] - Cy[:, 1])[None, :]
+            a = (D[:, 0] ** 2 + D[:, 1] ** 2)[:, None]
+            bq = 2.0 * (ox * D[:, 0:1] + oy * D[:, 1:2])
+            cq = ox * ox + oy * oy - (Cy[:, 2] ** 2)[None, :]
+            disc = bq * bq - 4.0 * a * cq
+            ok = (disc > 0) & (a > eps)
+            tt = (-bq - torch.sqrt(torch.where(ok, disc, torch.zeros_like(disc)))) / (2.0 * torch.where(ok, a.expand_as(disc), torch.ones_like(disc)))
+            z = O[2] + tt * D[:, 2:3]
+            hit = ok & (tt > 1e-6) & (z >= Cy[None, :, 3]) & (z <= Cy[None, :, 4])
+            tt = torch.where(hit, tt, torch.full_like(tt, float("inf")))
+            t_best = torch.minimum(t_best, tt.min(dim=1).values)
+    return t_best.cpu().numpy()
+
+
+def scan(scene: Scene, sensor: str, T_world_sensor: np.ndarray, rng: np.random.Generator, n_rays: int | None = None, min_range=0.5, max_range=100.0, noise=0.02, backend="numpy"):
     """One scan in the SENSOR frame: (points (N,4) float64 with w=1, times (N,) float64), time ordered."""
     d, t = sensor_pattern(sensor, rng, n_rays)
     R, o = T_world_sensor[:3, :3], T_world_sensor[:3, 3]
     dw = d @ R.T
-    rngs = _raycast(scene, o, dw, max_range)
+    rngs = _raycast_torch(scene, o, dw, max_range) if backend == "torch" else _raycast(scene, o, dw, max_range)
     rngs = rngs + rng.normal(0.0, noise, rngs.shape)
     ok = np.isfinite(rngs) & (rngs > min_range) & (rngs < max_range)
     p = d[ok] * rngs[ok, None]

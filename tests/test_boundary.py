@@ -1,0 +1,104 @@
+"""The drop-in boundary without a GPU: libglim_b200.so loads, exports exactly what include/glim_b200.h declares, and
+fails loudly (no CPU fallback) when there is no CUDA device.  Host logic of the multi-GPU sharding."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from glim_b200 import capi, multi_gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "glim_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return re.findall(r"GB_API\s+[\w\s\*]+?\b(gb_\w+)\s*\(", src)
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    declared = header_functions()
+    assert len(declared) >= 30
+    assert sorted(declared) == sorted(capi.SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_library_is_sm100a_only_and_links_no_torch():
+    out = os.popen(f"cuobjdump --list-elf {capi.SO_PATH} 2>/dev/null").read()
+    if out.strip():
+        archs = set(re.findall(r"sm_(\d+a?)", out))
+        assert archs == {"100a"}, archs
+    ldd = os.popen(f"ldd {capi.SO_PATH}").read()
+    assert "torch" not in ldd and "c10" not in ldd
+
+
+def test_status_strings():
+    L = capi.lib()
+    assert L.gb_status_string(0) == b"ok"
+    assert b"no CPU fallback" in L.gb_status_string(4)
+
+
+def test_no_device_fails_loudly():
+    L = capi.lib()
+    if L.gb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    h = C.c_void_p()
+    st = L.gb_ctx_create(0, C.byref(h))
+    assert st == 4 and not h.value  # GB_ERR_NO_DEVICE
+    assert b"no CPU fallback" in L.gb_last_error()
+    from glim_b200 import gpu
+
+    with pytest.raises(capi.GlimB200Error):
+        gpu.Context(0)
+    fr = C.c_size_t()
+    assert L.gb_mem_info(0, C.byref(fr), C.byref(fr)) == 4
+
+
+def test_null_arguments_are_rejected_not_crashed():
+    L = capi.lib()
+    assert L.gb_ctx_create(0, None) == 1
+    assert L.gb_cloud_size(None, None) == 1
+    assert L.gb_voxelmap_info(None, None, None, None) == 1
+    assert L.gb_sweep_launch(None) == 1
+    assert L.gb_ctx_destroy(None) == 0 and L.gb_cloud_destroy(None) == 0 and L.gb_vgicp_factor_destroy(None) == 0
+
+
+def test_pose16_is_column_major():
+    T = np.arange(16.0).reshape(4, 4)
+    assert np.array_equal(capi.pose16(T), T.T.reshape(16))
+    assert capi.pose16(np.stack([T, T])).shape == (2, 16)
+
+
+def test_lpt_partition_balances_and_is_deterministic():
+    rng = np.random.default_rng(0)
+    w = rng.integers(1000, 60000, size=301)
+    for parts in (1, 2, 4, 8):
+        p = multi_gpu.lpt_partition(w, parts)
+        loads = np.array([w[p == k].sum() for k in range(parts)])
+        assert loads.sum() == w.sum() and loads.max() <= loads.mean() + w.max()
+        assert np.array_equal(p, multi_gpu.lpt_partition(w, parts))
+
+
+def test_shard_factors_keeps_pairs_whole():
+    from glim_b200.workloads import Factor
+
+    factors = [Factor(i, l, j, pair) for pair, (i, j) in enumerate([(0, 3), (1, 3), (2, 3), (0, 4), (1, 4)]) for l in (0, 1)]
+    sizes = [50000, 40000, 30000, 50000, 20000]
+    f_rank, p_rank = multi_gpu.shard_factors(factors, sizes, 2)
+    for f, r in zip(factors, f_rank):
+        assert r == p_rank[f.pair]
+    assert set(f_rank) == {0, 1}
+
+
+def test_slab_row_roundtrip():
+    rng = np.random.default_rng(1)
+    A = rng.normal(size=(6, 6))
+    rec = {"H_tt": A @ A.T, "H_ss": A.T @ A, "H_ts": rng.normal(size=(6, 6)), "b_t": rng.normal(size=6), "b_s": rng.normal(size=6), "error": 3.5, "num_inliers": 42.0}
+    back = multi_gpu.unpack_slab_row(multi_gpu.pack_slab_row(rec))
+    for k in ("H_tt", "H_ss", "H_ts", "b_t", "b_s"):
+        assert np.allclose(back[k], rec[k], rtol=1e-6, atol=1e-6)
+    assert back["error"] == 3.5 and back["num_inliers"] == 42.0

@@ -1,0 +1,299 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (libglim_b200.so), against the CPU oracle
+on the same seeded inputs.  Bar (north_star): voxel coordinates / indices / inlier sets bit-exact, Hessians /
+gradients / errors within 1e-4 relative (Frobenius) of the fp64 oracle.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from glim_b200 import gpu, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = util.REL_TOL  # 1e-4, north_star
+
+
+@pytest.fixture(scope="module")
+def pair():
+    return util.scan_pair()
+
+
+@pytest.fixture(scope="module")
+def dev(ctx, pair):
+    """Clouds on the GPU + oracle twins of the device-layout data."""
+    d = {"cloud": [], "xyz": [], "cov6": []}
+    for P, Cv, N in zip(pair["points"], pair["covs"], pair["normals"]):
+        d["cloud"].append(gpu.PointCloudGPU.clone(P, Cv, N, ctx=ctx))
+        xyz, cov6 = oracle.pack_cloud(P, util.cov_colmajor16(Cv))
+        d["xyz"].append(xyz)
+        d["cov6"].append(cov6)
+    d["T_gt"] = synth.inv_pose(pair["poses"][0]) @ pair["poses"][1]
+    return d
+
+
+def check_linearized(got: dict, ref122: np.ndarray, tol=REL_TOL):
+    ref = oracle.split122(ref122)
+    assert got["num_inliers"] == ref["num_inliers"]  # inlier set bit-exact
+    for k in ("H_tt", "H_ss", "H_ts"):
+        assert util.rel_err(got[k], ref[k]) < tol, (k, util.rel_err(got[k], ref[k]))
+    # gradients are sums that cancel near the optimum: scale by the per-term magnitude sqrt(tr H * error)
+    for k, hk in (("b_t", "H_tt"), ("b_s", "H_ss")):
+        scale = max(np.linalg.norm(ref[k]), np.sqrt(np.trace(ref[hk]) * max(ref["error"], 1e-30)) * 1e-2)
+        assert np.linalg.norm(got[k] - ref[k]) < tol * scale, (k, np.linalg.norm(got[k] - ref[k]) / scale)
+    assert abs(got["error"] - ref["error"]) <= tol * abs(ref["error"]) + 1e-12
+
+
+def test_cloud_upload_is_bit_exact(dev):
+    for c, xyz, cov6 in zip(dev["cloud"], dev["xyz"], dev["cov6"]):
+        gx, gc = c.download()
+        assert np.array_equal(gx, xyz) and np.array_equal(gc, cov6)
+
+
+@pytest.mark.parametrize("res", [0.1, 0.25, 0.5, 1.0])
+def test_voxelmap_build_is_bit_exact(ctx, dev, res):
+    m = gpu.GaussianVoxelMapGPU(res, ctx=ctx).insert(dev["cloud"][0])
+    ref = oracle.GpuMap(dev["xyz"][0], dev["cov6"][0], res)
+    assert (m.num_voxels, m.num_buckets) == (ref.num_voxels, ref.num_buckets)
+    buckets, vnum, vmean, vcov = m.download()
+    assert np.array_equal(buckets, ref.buckets)  # coordinates, voxel numbering and bucket placement
+    assert np.array_equal(vnum, ref.vnum)
+    assert np.array_equal(vmean, ref.vmean) and np.array_equal(vcov, ref.vcov)  # fp32 sums in the same order
+
+
+def test_voxelmap_growth_loop_matches_oracle(ctx):
+    rng = synth.rng_for(12)
+    pts = rng.uniform(-200, 200, size=(60000, 3))
+    P = np.concatenate([pts, np.ones((len(pts), 1))], axis=1)
+    C = np.tile(np.diag([1.0, 1.0, 1.0, 0.0]), (len(P), 1, 1))
+    cloud = gpu.PointCloudGPU.clone(P, C, ctx=ctx)
+    xyz, cov6 = oracle.pack_cloud(P, util.cov_colmajor16(C))
+    for init in (1024, 16384):
+        m = gpu.GaussianVoxelMapGPU(0.5, init_num_buckets=init, ctx=ctx).insert(cloud)
+        ref = oracle.GpuMap(xyz, cov6, 0.5, init_buckets=init)
+        assert (m.num_voxels, m.num_buckets) == (ref.num_voxels, ref.num_buckets)
+        assert np.array_equal(m.download()[0], ref.buckets)
+
+
+@pytest.mark.parametrize("res", [0.25, 0.5, 0.1])
+def test_linearize_matches_oracle(ctx, dev, res):
+    m = gpu.GaussianVoxelMapGPU(res, ctx=ctx).insert(dev["cloud"][0])
+    ref_map = oracle.GpuMap(dev["xyz"][0], dev["cov6"][0], res)
+    # binary factor: keys 0 (target) and 1 (source)
+    fac = gpu.IntegratedVGICPFactorGPU(0, 1, m, dev["cloud"][1], ctx=ctx)
+    for T in util.test_poses(dev["T_gt"], 4, key=int(res * 100)):
+        got = fac.linearize({0: np.eye(4), 1: T})
+        ref, _ = oracle.linearize_gpumap(ref_map, dev["xyz"][1], dev["cov6"][1], T)
+        assert ref[121] > 0.3 * len(dev["xyz"][1])
+        check_linearized(got, ref)
+
+
+def test_linearize_adversarial_poses(ctx, dev):
+    """identity, 180 deg yaw, large translations (hash wrap, negative coordinates), no overlap at all."""
+    m = gpu.GaussianVoxelMapGPU(0.5, ctx=ctx).insert(dev["cloud"][0])
+    ref_map = oracle.GpuMap(dev["xyz"][0], dev["cov6"][0], 0.5)
+    fac = gpu.IntegratedVGICPFactorGPU(np.eye(4), 1, m, dev["cloud"][1], ctx=ctx)  # unary form
+    poses = [np.eye(4), synth.pose(0, 0, 0, np.pi), synth.pose(3.0, -2.0, 0.1, 0.3, 0.02, -0.01), synth.pose(-7.5, 4.25, 0.0, -2.0)]
+    for T in poses:
+        got = fac.linearize({1: T})
+        ref, _ = oracle.linearize_gpumap(ref_map, dev["xyz"][1], dev["cov6"][1], T)
+        check_linearized(got, ref)
+    far = synth.pose(5000.0, -3000.0, 100.0, 1.0)
+    got = fac.linearize({1: far})
+    assert got["num_inliers"] == 0 and got["error"] == 0 and not got["H_ss"].any()
+
+
+def test_unary_and_binary_forms_agree(ctx, dev):
+    m = gpu.GaussianVoxelMapGPU(0.5, ctx=ctx).insert(dev["cloud"][0])
+    Tt = synth.pose(10.0, -4.0, 0.5, 0.7, 0.01, 0.02)
+    Ts = Tt @ dev["T_gt"]
+    a = gpu.IntegratedVGICPFactorGPU(0, 1, m, dev["cloud"][1], ctx=ctx).linearize({0: Tt, 1: Ts})
+    b = gpu.IntegratedVGICPFactorGPU(Tt, 1, m, dev["cloud"][1], ctx=ctx).linearize({1: Ts})
+    for k in ("H_ss", "b_s", "H_tt"):
+        assert util.rel_err(a[k], b[k]) < 1e-6
+
+
+def test_error_matches_oracle(ctx, dev):
+    m = gpu.GaussianVoxelMapGPU(0.5, ctx=ctx).insert(dev["cloud"][0])
+    ref_map = oracle.GpuMap(dev["xyz"][0], dev["cov6"][0], 0.5)
+    fac = gpu.IntegratedVGICPFactorGPU(np.eye(4), 1, m, dev["cloud"][1], ctx=ctx)
+    T_lin = dev["T_gt"]
+    lin = fac.linearize({1: T_lin})
+    assert abs(fac.error({1: T_lin}) - lin["error"]) <= 1e-5 * lin["error"]
+    for T_eval in util.test_poses(dev["T_gt"], 3, key=5)[1:]:
+        e = fac.error({1: T_eval})
+        ref = oracle.error_gpumap(ref_map, dev["xyz"][1], dev["cov6"][1], T_lin, T_eval)
+        assert abs(e - ref) <= REL_TOL * ref
+
+
+def test_overlap_matches_oracle(ctx, dev):
+    maps = [gpu.GaussianVoxelMapGPU(r, ctx=ctx).insert(dev["cloud"][0]) for r in (0.5, 1.0)]
+    refs = [oracle.GpuMap(dev["xyz"][0], dev["cov6"][0], r) for r in (0.5, 1.0)]
+    T = dev["T_gt"]
+    far = synth.pose(900.0, 0, 0, 0)
+    assert gpu.overlap_gpu(maps[0], dev["cloud"][1], T) == oracle.overlap_gpumap([refs[0]], dev["xyz"][1], [T])
+    assert gpu.overlap_gpu(maps, dev["cloud"][1], [far, T]) == oracle.overlap_gpumap(refs, dev["xyz"][1], [far, T])
+    assert gpu.overlap_gpu(maps[0], dev["cloud"][1], far) == 0.0
+    T2 = synth.pose(6.0, 1.0, 0.0, 0.5)
+    assert gpu.overlap_gpu(maps, dev["cloud"][1], [T2, T]) == oracle.overlap_gpumap(refs, dev["xyz"][1], [T2, T])
+
+
+def test_factor_set_batch_equals_individual_and_is_repeatable(ctx, dev):
+    """NonlinearFactorSetGPU: one launch over several factors (two levels x two directions, ragged sizes, one empty
+    source) == per-factor calls; a second identical sweep gives identical bits (accumulators are self-cleaning)."""
+    maps0 = [gpu.GaussianVoxelMapGPU(r, ctx=ctx).insert(dev["cloud"][0]) for r in (0.25, 0.5)]
+    maps1 = [gpu.GaussianVoxelMapGPU(r, ctx=ctx).insert(dev["cloud"][1]) for r in (0.25, 0.5)]
+    empty = gpu.PointCloudGPU.clone(np.zeros((0, 4)), np.zeros((0, 4, 4)), ctx=ctx)
+    few = gpu.PointCloudGPU.clone(util.scan_pair()["points"][1][:777], util.scan_pair()["covs"][1][:777], ctx=ctx)
+    T = dev["T_gt"]
+    Ti = synth.inv_pose(T)
+    facs, deltas = [], []
+    for m in maps0:
+        facs.append(gpu.IntegratedVGICPFactorGPU(0, 1, m, dev["cloud"][1], ctx=ctx)); deltas.append(T)
+    for m in maps1:
+        facs.append(gpu.IntegratedVGICPFactorGPU(1, 0, m, dev["cloud"][0], ctx=ctx)); deltas.append(Ti)
+    facs.append(gpu.IntegratedVGICPFactorGPU(0, 1, maps0[1], empty, ctx=ctx)); deltas.append(T)
+    facs.append(gpu.IntegratedVGICPFactorGPU(0, 1, maps0[1], few, ctx=ctx)); deltas.append(T)
+    fs = gpu.NonlinearFactorSetGPU(ctx).add(facs)
+    deltas = np.stack(deltas)
+    a = fs.linearize_deltas(deltas)
+    b = fs.linearize_deltas(deltas)
+    assert a.tobytes() == b.tobytes()
+    assert a[4]["num_inliers"] == 0 and not np.asarray(a[4]["H_ss"]).any()
+    for i, f in enumerate(facs):
+        single = np.zeros(1, gpu.LIN_DTYPE)
+        from glim_b200.capi import check, lib, pose16, ptr
+        check(lib().gb_vgicp_linearize(f._handle(), ptr(pose16(deltas[i])), ptr(single)))
+        for k in ("H_tt", "H_ss", "H_ts", "b_t", "b_s"):
+            assert util.rel_err(np.asarray(a[i][k]), np.asarray(single[0][k])) < 1e-6 or not np.asarray(single[0][k]).any()
+        assert a[i]["num_inliers"] == single[0]["num_inliers"]
+    # against the oracle
+    ref_map = oracle.GpuMap(dev["xyz"][0], dev["cov6"][0], 0.25)
+    ref, _ = oracle.linearize_gpumap(ref_map, dev["xyz"][1], dev["cov6"][1], T)
+    check_linearized(gpu.unpack_linearized(a[0]), ref)
+    # error sweep
+    e = fs.error_deltas(deltas, deltas)
+    assert np.allclose(e, a["error"], rtol=1e-5)
+
+
+def test_pair_slab_accumulates_levels(ctx, dev):
+    import torch
+
+    maps0 = [gpu.GaussianVoxelMapGPU(r, ctx=ctx).insert(dev["cloud"][0]) for r in (0.25, 0.5)]
+    facs = [gpu.IntegratedVGICPFactorGPU(0, 1, m, dev["cloud"][1], ctx=ctx) for m in maps0]
+    sw = gpu.Sweep(ctx, facs, pair_index=[1, 1])
+    slab = torch.zeros((3, gpu.capi.GB_SLAB_STRIDE), dtype=torch.float32, device="cuda:0")
+    torch.cuda.synchronize()
+    sw.attach_slab(slab.data_ptr(), 3)
+    sw.set_poses(np.stack([dev["T_gt"]] * 2))
+    sw.launch()
+    rec = sw.fetch()
+    ctx.synchronize()
+    s = slab.cpu().numpy().astype(np.float64)
+    assert not s[0].any() and not s[2].any()
+    tot = {k: np.asarray(rec[0][k]) + np.asarray(rec[1][k]) for k in ("H_tt", "H_ss", "H_ts", "b_t", "b_s")}
+    iu = np.triu_indices(6)
+    Htt = tot["H_tt"].reshape(6, 6).T
+    Hss = tot["H_ss"].reshape(6, 6).T
+    assert np.allclose(s[1][0:21], Htt[iu], rtol=1e-6)
+    assert np.allclose(s[1][21:57], tot["H_ts"], rtol=1e-6, atol=1e-6 * np.abs(tot["H_ts"]).max())
+    assert np.allclose(s[1][57:78], Hss[iu], rtol=1e-6)
+    assert np.allclose(s[1][78:84], tot["b_t"], rtol=1e-5, atol=1e-6 * np.abs(tot["b_t"]).max())
+    assert np.allclose(s[1][84:90], tot["b_s"], rtol=1e-5, atol=1e-6 * np.abs(tot["b_s"]).max())
+    assert s[1][90] == pytest.approx(rec[0]["error"] + rec[1]["error"], rel=1e-6)
+    assert s[1][91] == rec[0]["num_inliers"] + rec[1]["num_inliers"]
+
+
+# ---------------------------------------------------------------------------------------------- preprocess kernels
+def test_covariances_match_oracle(ctx, pair):
+    from glim_b200 import preprocess
+
+    P = pair["points"][0]
+    nb = synth.knn(P, 10)
+    normals, covs = preprocess.CloudCovarianceEstimation(ctx=ctx).estimate(P, nb)
+    n_ref, c_ref = oracle.covariance_estimate(P, nb)
+    assert np.allclose(covs, c_ref, atol=1e-9)
+    assert np.allclose(normals, n_ref, atol=1e-9)
+    n5, c5 = preprocess.CloudCovarianceEstimation(ctx=ctx).estimate(P, nb, k_neighbors=5)
+    n5r, c5r = oracle.covariance_estimate(P, nb, k_neighbors=5)
+    assert np.allclose(c5, c5r, atol=1e-9)
+    e_n, e_c = preprocess.CloudCovarianceEstimation(ctx=ctx).estimate(np.zeros((0, 4)), np.zeros((0,), np.int32))
+    assert e_n.shape == (0, 4) and e_c.shape == (0, 4, 4)
+
+
+def test_find_neighbors_matches_oracle(ctx):
+    from glim_b200 import preprocess
+
+    P = util.scan_pair(n_rays=32 * 100)["points"][0]
+    for k in (10, 5, 20):
+        nb = preprocess.find_neighbors(P, k, ctx=ctx).reshape(len(P), k)
+        ref, _ = oracle.knn_bruteforce(P, k)
+        assert np.array_equal(nb, ref)  # identical distances (no FMA contraction) and tie rule -> identical indices
+    nb = preprocess.find_neighbors(P[:4], 10, ctx=ctx).reshape(4, 10)
+    assert (nb[:, 4:] == np.arange(4)[:, None]).all()
+
+
+def test_voxelgrid_sampling_matches_oracle(ctx, pair):
+    from glim_b200 import preprocess
+
+    P, T = pair["points"][0], pair["times"][0]
+    for res in (0.25, 0.1, 1.0):
+        out, ot, _ = preprocess.voxelgrid_sampling(P, res, times=T, ctx=ctx)
+        ref, rt, _ = oracle.voxelgrid_sampling(P, res, times=T)
+        assert np.array_equal(out, ref) and np.array_equal(ot, rt)  # same sums in the same order: bit-exact
+
+
+def test_preprocess_pipeline(ctx, pair):
+    """CloudPreprocessor::preprocess order (cloud_preprocessor.cpp:92-188): downsample -> range gate -> time sort -> k-NN."""
+    from glim_b200 import preprocess
+
+    P, T = pair["points"][0], pair["times"][0]
+    fr = preprocess.CloudPreprocessor(preprocess.CloudPreprocessorParams(downsample_resolution=0.3, distance_near_thresh=2.0, distance_far_thresh=30.0), ctx=ctx).preprocess(100.0, T, P)
+    d = np.linalg.norm(fr.points[:, :3], axis=1)
+    assert (d > 2.0).all() and (d < 30.0).all() and (np.diff(fr.times) >= 0).all()
+    assert fr.scan_end_time == 100.0 + fr.times[-1] and fr.neighbors.shape == (fr.size() * 10,)
+    ref_pts, ref_t, _ = oracle.voxelgrid_sampling(P, 0.3, times=T)
+    sq = (ref_pts[:, :3] ** 2).sum(1)
+    keep = (sq > 4.0) & (sq < 900.0)
+    assert fr.size() == keep.sum()
+    ref_nb, _ = oracle.knn_bruteforce(fr.points, 10)
+    assert np.array_equal(fr.neighbors.reshape(-1, 10), ref_nb)
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("sensor,n_rays,res", [("generic64", None, 0.5), ("os1_64", None, 0.25)])
+def test_full_size_properties(ctx, sensor, n_rays, res):
+    """BASELINE sizes (100 k / 130 k points) through size-independent properties: additivity over a split of the source
+    cloud, adjoint identities (A.4) on the returned blocks, symmetry / PSD, inliers == overlap * N, and the
+    oracle itself on the full input."""
+    sc = synth.make_hall_scene()
+    traj = synth.arc_trajectory(8)
+    clouds = []
+    for i in (3, 4):
+        pts, _ = synth.scan(sc, sensor, traj[i], synth.rng_for(55, i), n_rays=n_rays)
+        _, cov = synth.with_covariances(pts, 10)
+        clouds.append((pts, cov))
+    assert len(clouds[1][0]) > 90_000
+    tgt = gpu.PointCloudGPU.clone(*clouds[0], ctx=ctx)
+    m = gpu.GaussianVoxelMapGPU(res, ctx=ctx).insert(tgt)
+    P, Cv = clouds[1]
+    T = synth.perturb(synth.inv_pose(traj[3]) @ traj[4], synth.rng_for(56), 0.01, 0.05)
+    whole = gpu.IntegratedVGICPFactorGPU(np.eye(4), 1, m, gpu.PointCloudGPU.clone(P, Cv, ctx=ctx), ctx=ctx).linearize({1: T})
+    h = len(P) // 3
+    parts = [gpu.IntegratedVGICPFactorGPU(np.eye(4), 1, m, gpu.PointCloudGPU.clone(P[a:b], Cv[a:b], ctx=ctx), ctx=ctx).linearize({1: T}) for a, b in ((0, h), (h, len(P)))]
+    for k in ("H_tt", "H_ss", "H_ts", "b_t", "b_s"):
+        assert util.rel_err(parts[0][k] + parts[1][k], whole[k]) < 2e-5 or np.linalg.norm(parts[0][k] + parts[1][k] - whole[k]) < 2e-5 * np.sqrt(np.trace(whole["H_ss"]) * whole["error"])
+    assert parts[0]["num_inliers"] + parts[1]["num_inliers"] == whole["num_inliers"]
+    Tf = T.astype(np.float32).astype(np.float64)
+    Ad = np.zeros((6, 6))
+    Ad[:3, :3] = Tf[:3, :3]; Ad[3:, 3:] = Tf[:3, :3]; Ad[3:, :3] = synth.hat(Tf[:3, 3]) @ Tf[:3, :3]
+    assert util.rel_err(Ad.T @ whole["H_tt"] @ Ad, whole["H_ss"]) < 1e-9
+    assert util.rel_err(-whole["H_tt"] @ Ad, whole["H_ts"]) < 1e-9
+    assert np.linalg.eigvalsh(whole["H_ss"]).min() > 0
+    src = gpu.PointCloudGPU.clone(P, Cv, ctx=ctx)
+    assert gpu.overlap_gpu(m, src, T) * len(P) == pytest.approx(whole["num_inliers"], abs=0.5)
+    # and the oracle on the full-size input (a few seconds)
+    xyz0, cov0 = oracle.pack_cloud(clouds[0][0], util.cov_colmajor16(clouds[0][1]))
+    xyz1, cov1 = oracle.pack_cloud(P, util.cov_colmajor16(Cv))
+    ref, _ = oracle.linearize_gpumap(oracle.GpuMap(xyz0, cov0, res), xyz1, cov1, T)
+    check_linearized(whole, ref)
