@@ -57,7 +57,7 @@ def build_workload(name, ctx, scale, use_gpu):
     s = scale
     if name == "global_mapping_gpu":
         n = max(8, int(round(256 * s)) // 4 * 4)
-        return workloads.global_mapping(ctx, n_submaps=n, laps=4, use_gpu=use_gpu, n_rays=None if s >= 1 else 64 * max(64, int(2048 * s)),
+        return workloads.global_mapping(ctx, n_submaps=n, laps=4, side=300.0, use_gpu=use_gpu, n_rays=None if s >= 1 else 64 * max(64, int(2048 * s)),
                                         params=workloads.GlobalMappingParams(submap_target_num_points=max(2000, int(50000 * s))))
     if name == "odometry_gpu":
         n = max(6, int(round(64 * s)))

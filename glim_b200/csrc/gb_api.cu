@@ -312,6 +312,7 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   s->ctx = ctx; s->F = F; s->factors.assign(factors, factors + F);
   s->d_descs = nullptr; s->d_tiles = nullptr; s->d_poses = nullptr; s->d_poses_eval = nullptr; s->d_accum = nullptr; s->d_done = nullptr; s->d_out = nullptr;
   s->h_poses = nullptr; s->h_poses_eval = nullptr; s->h_out = nullptr; s->d_slab = nullptr; s->num_pairs = 0;
+  s->d_tile_ctr = nullptr; s->ctr_base = 0;
   s->num_tiles = 0; s->point_factors = 0; s->algorithmic_bytes = 0; s->key = 0; s->epoch = ctx->epoch;
 
   // tile size: enough tiles to balance the persistent grid, large enough to amortise the per-tile reduction
@@ -324,10 +325,10 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   const int capacity = ctx->num_sms * ctas_per_sm;
   int tile = env_int("GB_TILE", 0);
   if (tile <= 0) {
-    const uint64_t want = total_pts / ((uint64_t)capacity * 8) + 1;
+    const uint64_t want = total_pts / ((uint64_t)capacity * 12) + 1;
     tile = (int)std::min<uint64_t>(4096, std::max<uint64_t>(512, (want + 255) / 256 * 256));
   }
-  tile = (tile + 255) / 256 * 256;
+  tile = std::min(4096, std::max(256, (tile + 255) / 256 * 256));  // 8 warps x (32..512) points
   s->tile_size = tile;
 
   std::vector<FactorDesc> descs(F);
@@ -358,7 +359,7 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   if (F > 0) {
     // one device allocation, one pinned allocation
     const size_t b_desc = align_up(sizeof(FactorDesc) * F, 256), b_tiles = align_up(sizeof(int2) * tiles.size(), 256), b_pose = align_up(sizeof(double) * 16 * F, 256);
-    const size_t b_acc = align_up(sizeof(double) * GB_ACC_STRIDE * F, 256), b_done = align_up(sizeof(unsigned) * F, 256), b_out = align_up(sizeof(double) * GB_OUT_DOUBLES * F, 256);
+    const size_t b_acc = align_up(sizeof(double) * GB_ACC_STRIDE * F, 256), b_done = align_up(sizeof(unsigned) * F + 16, 256), b_out = align_up(sizeof(double) * GB_OUT_DOUBLES * F, 256);
     const size_t total = b_desc + b_tiles + 2 * b_pose + b_acc + b_done + b_out;
     char* d = nullptr;
     cudaError_t e = cudaMalloc((void**)&d, total);
@@ -368,7 +369,9 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     s->d_poses = (double*)d; d += b_pose;
     s->d_poses_eval = (double*)d; d += b_pose;
     s->d_accum = (double*)d; d += b_acc;
-    s->d_done = (unsigned*)d; d += b_done;
+    s->d_done = (unsigned*)d;
+    s->d_tile_ctr = (unsigned long long*)(d + align_up(sizeof(unsigned) * F, 8));
+    d += b_done;
     s->d_out = (double*)d;
     char* h = nullptr;
     e = cudaMallocHost((void**)&h, 2 * b_pose + b_out);

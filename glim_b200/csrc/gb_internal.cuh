@@ -103,6 +103,8 @@ struct gb_sweep {
   double* d_poses_eval;   // F x 16 (error mode)
   double* d_accum;        // F x GB_ACC_STRIDE, zero between sweeps (self-cleaning)
   unsigned* d_done;       // F tickets, zero between sweeps
+  unsigned long long* d_tile_ctr;  // dynamic tile queue head, monotonic across launches
+  unsigned long long ctr_base;     // value of the counter at the start of the next launch
   double* d_out;          // F x 122
   double* h_poses;        // pinned
   double* h_poses_eval;   // pinned

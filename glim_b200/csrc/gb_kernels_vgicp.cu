@@ -162,55 +162,118 @@ __device__ void factor_epilogue(int f, const FactorDesc& D, const double* __rest
   if (lane == 7) { o[121] = A[28]; if (srow) atomicAdd(&srow[91], (float)A[28]); }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The sweep kernel.  Persistent grid, dynamic tile queue (one global atomic per tile, monotonic
+// across launches so it never needs a reset).  A tile = kWarps x `sub` consecutive source points of
+// one factor; every warp owns `sub` of them and runs two warp-local phases:
+//   A (lookup, all lanes busy): 16-byte read of (x, y, z, c00), transform, voxel coordinate, hash
+//     probe; hits are COMPACTED into the warp's shared-memory queue as (point, voxel) pairs with
+//     ballot + popc, in point order (deterministic).
+//   B (derivatives, dense): lanes walk the queue, so warps stay full whatever the inlier rate;
+//     only hits pay for the remaining 20 bytes of the source point, the 48-byte voxel record and
+//     the ~180-instruction Mahalanobis / Hessian update.
+// This is the reference's lookup-pass / compaction / derivative-pass structure, but the inlier list
+// lives in shared memory for the lifetime of one tile instead of making a round trip through HBM.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSubMax = 512;   // queue capacity per warp (points per warp per tile)
+constexpr int kLookupUnroll = 4;
+
+__device__ __forceinline__ PoseF pose_from_colmajor(const double* __restrict__ T) {
+  PoseF P;
+  P.r00 = (float)T[0]; P.r01 = (float)T[4]; P.r02 = (float)T[8];  P.tx = (float)T[12];
+  P.r10 = (float)T[1]; P.r11 = (float)T[5]; P.r12 = (float)T[9];  P.ty = (float)T[13];
+  P.r20 = (float)T[2]; P.r21 = (float)T[6]; P.r22 = (float)T[10]; P.tz = (float)T[14];
+  return P;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep(
   const FactorDesc* __restrict__ descs, const double* __restrict__ poses, const double* __restrict__ poses_eval,
-  const int2* __restrict__ tiles, int num_tiles, int tile_size,
+  const int2* __restrict__ tiles, int num_tiles, int sub,
+  unsigned long long* __restrict__ tile_ctr, unsigned long long ctr_base,
   double* __restrict__ accum, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab) {
-  __shared__ float s_pose[24];
+  __shared__ uint2 s_q[kWarps][kSubMax];
   __shared__ float s_red[kWarps][32];
   __shared__ double s_epi[144];
+  __shared__ int s_tile;
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  if (tid == 0) s_tile = (int)(atomicAdd(tile_ctr, 1ull) - ctr_base);
+  __syncthreads();
+  int tile = s_tile;
+
+  while (tile < num_tiles) {
+    int next_tile = 0;
+    if (tid == 0) next_tile = (int)(atomicAdd(tile_ctr, 1ull) - ctr_base);  // latency hidden behind the tile
     const int2 tl = __ldg(&tiles[tile]);
     const int f = tl.x;
     const FactorDesc D = descs[f];
     // pose -> fp32 row-major R | t  (Isometry3f cast of the reference GPU factor)
-    if (tid < 12) {
-      const double* T = poses + (size_t)f * 16;
-      const int r = tid < 9 ? tid / 3 : tid - 9, c = tid < 9 ? tid % 3 : 3;
-      s_pose[tid] = (float)T[c * 4 + r];
-      if (MODE == GB_MODE_ERROR) {
-        const double* Te = poses_eval + (size_t)f * 16;
-        s_pose[12 + tid] = (float)Te[c * 4 + r];
+    const PoseF P = pose_from_colmajor(poses + (size_t)f * 16);
+    const int tile_end = min(tl.y + kWarps * sub, D.n);
+    const int wb = min(tl.y + warp * sub, tile_end);
+    const int we = min(wb + sub, tile_end);
+
+    // ---------------- phase A: lookup + compaction ----------------
+    int nq = 0;  // warp-uniform queue length
+    for (int i0 = wb; i0 < we; i0 += 32 * kLookupUnroll) {
+      int cx[kLookupUnroll], cy[kLookupUnroll], cz[kLookupUnroll];
+      uint32_t h[kLookupUnroll];
+      int4 b[kLookupUnroll];
+#pragma unroll
+      for (int u = 0; u < kLookupUnroll; u++) {
+        const int i = i0 + u * 32 + lane;
+        const float4 a0 = __ldg(&D.p0[min(i, we - 1)]);
+        float qx, qy, qz;
+        transform(P, a0.x, a0.y, a0.z, qx, qy, qz);
+        cx[u] = gb_coord(qx, D.inv_res); cy[u] = gb_coord(qy, D.inv_res); cz[u] = gb_coord(qz, D.inv_res);
+        h[u] = gb_hash(cx[u], cy[u], cz[u]);
+        b[u] = __ldg(&D.buckets[h[u] & D.mask]);
+      }
+#pragma unroll
+      for (int u = 0; u < kLookupUnroll; u++) {
+        const int i = i0 + u * 32 + lane;
+        int v = -1;
+        if (b[u].w >= 0) {
+          if (b[u].x == cx[u] && b[u].y == cy[u] && b[u].z == cz[u]) {
+            v = b[u].w;
+          } else {
+            for (int k = 1; k < D.max_scan; k++) {  // rare: collision chain
+              const int4 bb = __ldg(&D.buckets[(h[u] + (uint32_t)k) & D.mask]);
+              if (bb.w < 0) break;
+              if (bb.x == cx[u] && bb.y == cy[u] && bb.z == cz[u]) { v = bb.w; break; }
+            }
+          }
+        }
+        if (i >= we) v = -1;
+        const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
+        if (v >= 0) s_q[warp][nq + __popc(m & lt_mask)] = make_uint2((unsigned)i, (unsigned)v);
+        nq += __popc(m);
       }
     }
-    __syncthreads();
-    const PoseF P = load_pose(s_pose);
-    PoseF Pe = P;
-    if (MODE == GB_MODE_ERROR) Pe = load_pose(s_pose + 12);
+    __syncwarp();
 
+    // ---------------- phase B: dense derivative pass over the warp's inliers ----------------
+    PoseF Pe = P;
+    if (MODE == GB_MODE_ERROR) Pe = pose_from_colmajor(poses_eval + (size_t)f * 16);
     float acc[32];
 #pragma unroll
     for (int k = 0; k < 32; k++) acc[k] = 0.f;
 
-    const int begin = tl.y;
-    const int end = min(begin + tile_size, D.n);
-    for (int i = begin + tid; i < end; i += kThreads) {
+#pragma unroll 2
+    for (int k = lane; k < nq; k += 32) {
+      const uint2 e = s_q[warp][k];
+      const int i = (int)e.x;
       const float4 a0 = __ldg(&D.p0[i]);
       const float4 a1 = __ldg(&D.p1[i]);
       const float a2 = __ldg(&D.p2[i]);
+      const float4 v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]);
+      const float4 v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]);
+      const float4 v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
       float qx, qy, qz;
-      transform(P, a0.x, a0.y, a0.z, qx, qy, qz);
-      const int cx = gb_coord(qx, D.inv_res), cy = gb_coord(qy, D.inv_res), cz = gb_coord(qz, D.inv_res);
-      const int v = gb_lookup(D.buckets, D.mask, D.max_scan, cx, cy, cz);
-      if (v < 0) continue;
-      const float4 v0 = __ldg(&D.voxels[3 * (size_t)v + 0]);
-      const float4 v1 = __ldg(&D.voxels[3 * (size_t)v + 1]);
-      const float4 v2 = __ldg(&D.voxels[3 * (size_t)v + 2]);
-      if (MODE == GB_MODE_ERROR) transform(Pe, a0.x, a0.y, a0.z, qx, qy, qz);
+      transform(Pe, a0.x, a0.y, a0.z, qx, qy, qz);
       float mxx, mxy, mxz, myy, myz, mzz;
       fused_mahalanobis(Pe, a0.w, a1.x, a1.y, a1.z, a1.w, a2, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, mxx, mxy, mxz, myy, myz, mzz);
       const float rx = v0.x - qx, ry = v0.y - qy, rz = v0.z - qz;
@@ -243,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep(
       }
     }
 
-    // ---- tile reduction ----
+    // ---------------- tile reduction ----------------
     if (MODE == GB_MODE_LINEARIZE) {
       const float r = warp_reduce_scatter32(acc, lane);
       s_red[warp][lane] = r;
@@ -268,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep(
         const unsigned ticket = atomicAdd(&done[f], 1u);
         s_last = (ticket == (unsigned)D.num_tiles - 1u);
         if (s_last) done[f] = 0u;  // self-cleaning
+        s_tile = next_tile;
       }
       __syncwarp();
       if (s_last) {
@@ -275,7 +339,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep(
         factor_epilogue(f, D, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, out, slab, s_epi);
       }
     }
-    __syncthreads();  // s_pose / s_red / s_last are reused by the next tile
+    __syncthreads();
+    tile = s_tile;
   }
 }
 
@@ -312,10 +377,12 @@ gb_status gb_launch_sweep(gb_sweep* s, int mode) {
   if (s->num_tiles == 0) return GB_OK;
   gb_ctx* ctx = s->ctx;
   if (mode == GB_MODE_LINEARIZE)
-    k_vgicp_sweep<GB_MODE_LINEARIZE><<<s->grid, kThreads, 0, ctx->stream>>>(s->d_descs, s->d_poses, nullptr, s->d_tiles, s->num_tiles, s->tile_size, s->d_accum, s->d_done, s->d_out, s->d_slab);
+    k_vgicp_sweep<GB_MODE_LINEARIZE><<<s->grid, kThreads, 0, ctx->stream>>>(s->d_descs, s->d_poses, nullptr, s->d_tiles, s->num_tiles, s->tile_size / kWarps, s->d_tile_ctr, s->ctr_base, s->d_accum, s->d_done, s->d_out, s->d_slab);
   else
-    k_vgicp_sweep<GB_MODE_ERROR><<<s->grid, kThreads, 0, ctx->stream>>>(s->d_descs, s->d_poses, s->d_poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_accum, s->d_done, s->d_out, nullptr);
+    k_vgicp_sweep<GB_MODE_ERROR><<<s->grid, kThreads, 0, ctx->stream>>>(s->d_descs, s->d_poses, s->d_poses_eval, s->d_tiles, s->num_tiles, s->tile_size / kWarps, s->d_tile_ctr, s->ctr_base, s->d_accum, s->d_done, s->d_out, nullptr);
   GB_CUDA(cudaGetLastError());
+  // every CTA draws tickets until it gets one past the end: the counter advances by num_tiles + grid per launch
+  s->ctr_base += (unsigned long long)s->num_tiles + (unsigned long long)s->grid;
   ctx->launches++;
   return GB_OK;
 }
