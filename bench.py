@@ -420,7 +420,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.workload, w, {"parallelism": (f"pairs sharded over {world} rank(s), NCCL all-reduce of the [{slabs[0].shape[0]} x {GB_SLAB_STRIDE}] fp32 Hessian slab" if sharded else f"replicas x{world} (single online stream does not shard)"),
-                                                       "tile_size": [int(sweeps[0].num_tiles), int(sweeps[0].grid)], "build_seconds": round(build_s, 1), "scale": args.scale}),
+                                                       "tiles_grid_first_sweep": [int(sweeps[0].num_tiles), int(sweeps[0].grid)], "build_seconds": round(build_s, 1), "scale": args.scale}),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ems / e_steps},
             "gpu_launches": int(gpu_launches),
             "clocks": sampler.summary(t0, t1) if sampler else None,

@@ -325,8 +325,10 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   const int capacity = ctx->num_sms * ctas_per_sm;
   int tile = env_int("GB_TILE", 0);
   if (tile <= 0) {
-    const uint64_t want = total_pts / ((uint64_t)capacity * 12) + 1;
-    tile = (int)std::min<uint64_t>(4096, std::max<uint64_t>(512, (want + 255) / 256 * 256));
+    // small sweeps: one balanced tile per CTA (the per-tile reduction is paid once); large sweeps: 4096-point tiles
+    // handed out dynamically
+    const uint64_t want = (total_pts + (uint64_t)capacity - 1) / (uint64_t)capacity;
+    tile = (int)std::min<uint64_t>(4096, std::max<uint64_t>(256, (want + 255) / 256 * 256));
   }
   tile = std::min(4096, std::max(256, (tile + 255) / 256 * 256));  // 8 warps x (32..512) points
   s->tile_size = tile;

@@ -145,6 +145,8 @@ def single_pair(ctx, n_rays=None, sensor="generic64", num_draws=16, use_gpu=Fals
         w.host_clouds.append(make_scan(sc, sensor, traj[i], synth.rng_for(101, i), n_rays=n_rays, ctx=ctx, use_gpu=use_gpu))
         w.poses.append(traj[i])
     w.resolutions = [0.5]  # vgicp_resolution 0.5, vgicp_voxelmap_levels 1 (config_odometry_cpu.json:30-31)
+    w.upload()
+    w.build_maps(which={0})
     rng = synth.rng_for(102)
     # unary form, fixed target pose (odometry_estimation_cpu.cpp:107: IntegratedVGICPFactor(gtsam::Pose3(), X(current), ...))
     for _ in range(num_draws):
