@@ -325,12 +325,13 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   const int capacity = ctx->num_sms * ctas_per_sm;
   int tile = env_int("GB_TILE", 0);
   if (tile <= 0) {
-    // small sweeps: one balanced tile per CTA (the per-tile reduction is paid once); large sweeps: 4096-point tiles
-    // handed out dynamically
-    const uint64_t want = (total_pts + (uint64_t)capacity - 1) / (uint64_t)capacity;
-    tile = (int)std::min<uint64_t>(4096, std::max<uint64_t>(256, (want + 255) / 256 * 256));
+    // work items are per WARP.  Small sweeps: one balanced item per warp (the per-item reduction is paid once);
+    // large sweeps: 2048-point items handed out dynamically
+    const uint64_t warps = (uint64_t)capacity * 8;
+    const uint64_t want = (total_pts + warps - 1) / warps;
+    tile = (int)std::min<uint64_t>(2048, std::max<uint64_t>(128, (want + 31) / 32 * 32));
   }
-  tile = std::min(4096, std::max(256, (tile + 255) / 256 * 256));  // 8 warps x (32..512) points
+  tile = std::min(1 << 20, std::max(32, (tile + 31) / 32 * 32));
   s->tile_size = tile;
 
   std::vector<FactorDesc> descs(F);
@@ -356,7 +357,7 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     s->algorithmic_bytes += (uint64_t)D.n * (48 + ((fa->flags & GB_FACTOR_SURFACE_VALIDATION) ? 12 : 0)) + (uint64_t)fa->target->num_voxels * 48 + (uint64_t)fa->target->num_buckets * 16 + 64 + 488;
   }
   s->num_tiles = (int)tiles.size();
-  s->grid = std::max(1, std::min(s->num_tiles, capacity));
+  s->grid = std::max(1, std::min((s->num_tiles + 7) / 8, capacity));
 
   if (F > 0) {
     // one device allocation, one pinned allocation

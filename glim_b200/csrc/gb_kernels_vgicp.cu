@@ -6,19 +6,19 @@
 // gtsam_points::overlap_gpu (odometry_estimation_gpu.cpp:231,248).  Math: SURVEY.md Appendix A;
 // oracle: go_vgicp_linearize_gpumap / go_vgicp_error_gpumap / go_overlap_gpumap (oracle/glim_oracle.c).
 //
-// One launch covers a whole factor set.  Work unit = a tile of `tile_size` consecutive source
-// points of one factor; tiles are laid out factor-major and handed to a persistent grid
-// round-robin, so at any instant the grid works on a window of a few consecutive factors whose
-// source cloud and voxel table stay L2 resident.  Per point (one thread):
-//   coalesced 36-byte read of (mean, packed covariance) -> q = R a + t -> voxel coord -> hash probe
-//   (16-byte buckets) -> 48-byte voxel record -> S = C_B + R C_A R^T, M = S^-1 (symmetric 3x3)
-//   -> accumulate the 21 unique entries of H_tt = J_t^T M J_t (J_t = [-hat(q) | I]), the 6 of
-//   b_t = J_t^T M r, the error r^T M r and the inlier count: 29 registers.
-// Per tile: transposing warp reduce-scatter (31 shuffles for 32 values), cross-warp sum in shared
-// memory, 29 fp64 atomics into the factor's accumulator.  The CTA that retires a factor's last
-// tile runs the fp64 epilogue: H_ts = -H_tt Ad, H_ss = Ad^T H_tt Ad, b_s = -Ad^T b_t with
-// Ad = AdjointMap(delta), writes the 122-double record (and adds it to the pair
-// slab when one is attached), and re-zeroes the accumulator for the next sweep.
+// One launch covers a whole factor set.  Work unit = an item of up to `chunk` consecutive source
+// points of one factor; items are laid out factor-major and drawn from a global queue by the warps of
+// a persistent grid, so at any instant the grid works on a window of a few consecutive factors whose
+// source cloud and voxel table stay L2 resident.  Per inlier (one lane):
+//   q = R a + t -> voxel coord -> hash probe (16-byte buckets) -> 48-byte voxel record ->
+//   S = C_B + R C_A R^T, M = S^-1 (symmetric 3x3) -> accumulate the 21 unique entries of
+//   H_tt = J_t^T M J_t (J_t = [-hat(q) | I]), the 6 of b_t = J_t^T M r, the error r^T M r and the
+//   inlier count: 29 registers.
+// Per item: transposing warp reduce-scatter (31 shuffles for 32 values) and 29 fp64 atomics into the
+// factor's accumulator.  The warp that retires a factor's last item runs the fp64 epilogue:
+// H_ts = -H_tt Ad, H_ss = Ad^T H_tt Ad, b_s = -Ad^T b_t with Ad = AdjointMap(delta),
+// writes the 122-double record (and adds it to the pair slab when one is attached), and re-zeroes
+// the accumulator for the next sweep.
 #include "gb_internal.cuh"
 
 namespace {
@@ -163,19 +163,23 @@ __device__ void factor_epilogue(int f, const FactorDesc& D, const double* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// The sweep kernel.  Persistent grid, dynamic tile queue (one global atomic per tile, monotonic
-// across launches so it never needs a reset).  A tile = kWarps x `sub` consecutive source points of
-// one factor; every warp owns `sub` of them and runs two warp-local phases:
+// The sweep kernel.  Persistent grid of independent WARPS: every warp draws work items from a
+// global queue (one atomic per item; the counter is monotonic across launches so it never needs a
+// reset).  An item = up to `chunk` consecutive source points of one factor, processed in rounds of
+// kSubMax points with two warp-local phases:
 //   A (lookup, all lanes busy): 16-byte read of (x, y, z, c00), transform, voxel coordinate, hash
 //     probe; hits are COMPACTED into the warp's shared-memory queue as (point, voxel) pairs with
 //     ballot + popc, in point order (deterministic).
-//   B (derivatives, dense): lanes walk the queue, so warps stay full whatever the inlier rate;
+//   B (derivatives, dense): lanes walk the queue, so the warp stays full whatever the inlier rate;
 //     only hits pay for the remaining 20 bytes of the source point, the 48-byte voxel record and
 //     the ~180-instruction Mahalanobis / Hessian update.
 // This is the reference's lookup-pass / compaction / derivative-pass structure, but the inlier list
-// lives in shared memory for the lifetime of one tile instead of making a round trip through HBM.
+// lives in shared memory for the lifetime of one round instead of making a round trip through HBM.
+// There is no block-level synchronisation anywhere: the item ends with a transposing warp
+// reduce-scatter (31 shuffles) and 29 fp64 atomics into the factor's accumulator; the warp that
+// retires a factor's last item runs its fp64 epilogue.
 // ---------------------------------------------------------------------------------------------
-constexpr int kSubMax = 512;   // queue capacity per warp (points per warp per tile)
+constexpr int kSubMax = 512;   // queue capacity per warp (points per round)
 constexpr int kLookupUnroll = 4;
 
 __device__ __forceinline__ PoseF pose_from_colmajor(const double* __restrict__ T) {
@@ -189,158 +193,148 @@ __device__ __forceinline__ PoseF pose_from_colmajor(const double* __restrict__ T
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep(
   const FactorDesc* __restrict__ descs, const double* __restrict__ poses, const double* __restrict__ poses_eval,
-  const int2* __restrict__ tiles, int num_tiles, int sub,
-  unsigned long long* __restrict__ tile_ctr, unsigned long long ctr_base,
+  const int2* __restrict__ items, int num_items, int chunk,
+  unsigned long long* __restrict__ item_ctr, unsigned long long ctr_base,
   double* __restrict__ accum, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab) {
-  __shared__ uint2 s_q[kWarps][kSubMax];
-  __shared__ float s_red[kWarps][32];
-  __shared__ double s_epi[144];
-  __shared__ int s_tile;
-  __shared__ int s_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ __align__(16) uint2 s_q[kWarps][kSubMax];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
+  uint2* __restrict__ q = s_q[warp];
 
-  if (tid == 0) s_tile = (int)(atomicAdd(tile_ctr, 1ull) - ctr_base);
-  __syncthreads();
-  int tile = s_tile;
+  int item = 0;
+  if (lane == 0) item = (int)(atomicAdd(item_ctr, 1ull) - ctr_base);
+  item = __shfl_sync(0xffffffffu, item, 0);
 
-  while (tile < num_tiles) {
-    int next_tile = 0;
-    if (tid == 0) next_tile = (int)(atomicAdd(tile_ctr, 1ull) - ctr_base);  // latency hidden behind the tile
-    const int2 tl = __ldg(&tiles[tile]);
-    const int f = tl.x;
+  while (item < num_items) {
+    int next_item = 0;
+    if (lane == 0) next_item = (int)(atomicAdd(item_ctr, 1ull) - ctr_base);  // latency hidden behind the item
+    const int2 it = __ldg(&items[item]);
+    const int f = it.x;
     const FactorDesc D = descs[f];
     // pose -> fp32 row-major R | t  (Isometry3f cast of the reference GPU factor)
     const PoseF P = pose_from_colmajor(poses + (size_t)f * 16);
-    const int tile_end = min(tl.y + kWarps * sub, D.n);
-    const int wb = min(tl.y + warp * sub, tile_end);
-    const int we = min(wb + sub, tile_end);
-
-    // ---------------- phase A: lookup + compaction ----------------
-    int nq = 0;  // warp-uniform queue length
-    for (int i0 = wb; i0 < we; i0 += 32 * kLookupUnroll) {
-      int cx[kLookupUnroll], cy[kLookupUnroll], cz[kLookupUnroll];
-      uint32_t h[kLookupUnroll];
-      int4 b[kLookupUnroll];
-#pragma unroll
-      for (int u = 0; u < kLookupUnroll; u++) {
-        const int i = i0 + u * 32 + lane;
-        const float4 a0 = __ldg(&D.p0[min(i, we - 1)]);
-        float qx, qy, qz;
-        transform(P, a0.x, a0.y, a0.z, qx, qy, qz);
-        cx[u] = gb_coord(qx, D.inv_res); cy[u] = gb_coord(qy, D.inv_res); cz[u] = gb_coord(qz, D.inv_res);
-        h[u] = gb_hash(cx[u], cy[u], cz[u]);
-        b[u] = __ldg(&D.buckets[h[u] & D.mask]);
-      }
-#pragma unroll
-      for (int u = 0; u < kLookupUnroll; u++) {
-        const int i = i0 + u * 32 + lane;
-        int v = -1;
-        if (b[u].w >= 0) {
-          if (b[u].x == cx[u] && b[u].y == cy[u] && b[u].z == cz[u]) {
-            v = b[u].w;
-          } else {
-            for (int k = 1; k < D.max_scan; k++) {  // rare: collision chain
-              const int4 bb = __ldg(&D.buckets[(h[u] + (uint32_t)k) & D.mask]);
-              if (bb.w < 0) break;
-              if (bb.x == cx[u] && bb.y == cy[u] && bb.z == cz[u]) { v = bb.w; break; }
-            }
-          }
-        }
-        if (i >= we) v = -1;
-        const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
-        if (v >= 0) s_q[warp][nq + __popc(m & lt_mask)] = make_uint2((unsigned)i, (unsigned)v);
-        nq += __popc(m);
-      }
-    }
-    __syncwarp();
-
-    // ---------------- phase B: dense derivative pass over the warp's inliers ----------------
     PoseF Pe = P;
     if (MODE == GB_MODE_ERROR) Pe = pose_from_colmajor(poses_eval + (size_t)f * 16);
+    const int item_end = min(it.y + chunk, D.n);
+
     float acc[32];
 #pragma unroll
     for (int k = 0; k < 32; k++) acc[k] = 0.f;
 
-#pragma unroll 2
-    for (int k = lane; k < nq; k += 32) {
-      const uint2 e = s_q[warp][k];
-      const int i = (int)e.x;
-      const float4 a0 = __ldg(&D.p0[i]);
-      const float4 a1 = __ldg(&D.p1[i]);
-      const float a2 = __ldg(&D.p2[i]);
-      const float4 v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]);
-      const float4 v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]);
-      const float4 v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
-      float qx, qy, qz;
-      transform(Pe, a0.x, a0.y, a0.z, qx, qy, qz);
-      float mxx, mxy, mxz, myy, myz, mzz;
-      fused_mahalanobis(Pe, a0.w, a1.x, a1.y, a1.z, a1.w, a2, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, mxx, mxy, mxz, myy, myz, mzz);
-      const float rx = v0.x - qx, ry = v0.y - qy, rz = v0.z - qz;
-      const float wx = mxx * rx + mxy * ry + mxz * rz;
-      const float wy = mxy * rx + myy * ry + myz * rz;
-      const float wz = mxz * rx + myz * ry + mzz * rz;
-      acc[27] += rx * wx + ry * wy + rz * wz;
-      acc[28] += 1.0f;
-      if (MODE == GB_MODE_LINEARIZE) {
-        // G = hat(q) M   (rows: rotation, cols: translation block of H_tt)
-        const float g00 = qy * mxz - qz * mxy, g01 = qy * myz - qz * myy, g02 = qy * mzz - qz * myz;
-        const float g10 = qz * mxx - qx * mxz, g11 = qz * mxy - qx * myz, g12 = qz * mxz - qx * mzz;
-        const float g20 = qx * mxy - qy * mxx, g21 = qx * myy - qy * mxy, g22 = qx * myz - qy * mxz;
-        // H_rr = G hat(q)^T : row i = q x g_i   (upper triangle)
-        acc[0] += qy * g02 - qz * g01;
-        acc[1] += qz * g00 - qx * g02;
-        acc[2] += qx * g01 - qy * g00;
-        acc[3] += g00; acc[4] += g01; acc[5] += g02;
-        acc[6] += qz * g10 - qx * g12;
-        acc[7] += qx * g11 - qy * g10;
-        acc[8] += g10; acc[9] += g11; acc[10] += g12;
-        acc[11] += qx * g21 - qy * g20;
-        acc[12] += g20; acc[13] += g21; acc[14] += g22;
-        acc[15] += mxx; acc[16] += mxy; acc[17] += mxz; acc[18] += myy; acc[19] += myz; acc[20] += mzz;
-        // b_t = [q x w ; w]
-        acc[21] += qy * wz - qz * wy;
-        acc[22] += qz * wx - qx * wz;
-        acc[23] += qx * wy - qy * wx;
-        acc[24] += wx; acc[25] += wy; acc[26] += wz;
+    for (int wb = it.y; wb < item_end; wb += kSubMax) {
+      const int we = min(wb + kSubMax, item_end);
+      // ---------------- phase A: lookup + compaction ----------------
+      int nq = 0;  // warp-uniform queue length
+      for (int i0 = wb; i0 < we; i0 += 32 * kLookupUnroll) {
+        int cx[kLookupUnroll], cy[kLookupUnroll], cz[kLookupUnroll];
+        uint32_t h[kLookupUnroll];
+        int4 b[kLookupUnroll];
+#pragma unroll
+        for (int u = 0; u < kLookupUnroll; u++) {
+          const int i = i0 + u * 32 + lane;
+          const float4 a0 = __ldg(&D.p0[min(i, we - 1)]);
+          float qx, qy, qz;
+          transform(P, a0.x, a0.y, a0.z, qx, qy, qz);
+          cx[u] = gb_coord(qx, D.inv_res); cy[u] = gb_coord(qy, D.inv_res); cz[u] = gb_coord(qz, D.inv_res);
+          h[u] = gb_hash(cx[u], cy[u], cz[u]);
+          b[u] = __ldg(&D.buckets[h[u] & D.mask]);
+        }
+#pragma unroll
+        for (int u = 0; u < kLookupUnroll; u++) {
+          const int i = i0 + u * 32 + lane;
+          int v = -1;
+          if (b[u].w >= 0) {
+            if (b[u].x == cx[u] && b[u].y == cy[u] && b[u].z == cz[u]) {
+              v = b[u].w;
+            } else {
+              for (int k = 1; k < D.max_scan; k++) {  // rare: collision chain
+                const int4 bb = __ldg(&D.buckets[(h[u] + (uint32_t)k) & D.mask]);
+                if (bb.w < 0) break;
+                if (bb.x == cx[u] && bb.y == cy[u] && bb.z == cz[u]) { v = bb.w; break; }
+              }
+            }
+          }
+          if (i >= we) v = -1;
+          const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
+          if (v >= 0) q[nq + __popc(m & lt_mask)] = make_uint2((unsigned)i, (unsigned)v);
+          nq += __popc(m);
+        }
       }
+      __syncwarp();
+
+      // ---------------- phase B: dense derivative pass over the round's inliers ----------------
+#pragma unroll 2
+      for (int k = lane; k < nq; k += 32) {
+        const uint2 e = q[k];
+        const int i = (int)e.x;
+        const float4 a0 = __ldg(&D.p0[i]);
+        const float4 a1 = __ldg(&D.p1[i]);
+        const float a2 = __ldg(&D.p2[i]);
+        const float4 v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]);
+        const float4 v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]);
+        const float4 v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
+        float qx, qy, qz;
+        transform(Pe, a0.x, a0.y, a0.z, qx, qy, qz);
+        float mxx, mxy, mxz, myy, myz, mzz;
+        fused_mahalanobis(Pe, a0.w, a1.x, a1.y, a1.z, a1.w, a2, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, mxx, mxy, mxz, myy, myz, mzz);
+        const float rx = v0.x - qx, ry = v0.y - qy, rz = v0.z - qz;
+        const float wx = mxx * rx + mxy * ry + mxz * rz;
+        const float wy = mxy * rx + myy * ry + myz * rz;
+        const float wz = mxz * rx + myz * ry + mzz * rz;
+        acc[27] += rx * wx + ry * wy + rz * wz;
+        acc[28] += 1.0f;
+        if (MODE == GB_MODE_LINEARIZE) {
+          // G = hat(q) M   (rows: rotation, cols: translation block of H_tt)
+          const float g00 = qy * mxz - qz * mxy, g01 = qy * myz - qz * myy, g02 = qy * mzz - qz * myz;
+          const float g10 = qz * mxx - qx * mxz, g11 = qz * mxy - qx * myz, g12 = qz * mxz - qx * mzz;
+          const float g20 = qx * mxy - qy * mxx, g21 = qx * myy - qy * mxy, g22 = qx * myz - qy * mxz;
+          // H_rr = G hat(q)^T : row i = q x g_i   (upper triangle)
+          acc[0] += qy * g02 - qz * g01;
+          acc[1] += qz * g00 - qx * g02;
+          acc[2] += qx * g01 - qy * g00;
+          acc[3] += g00; acc[4] += g01; acc[5] += g02;
+          acc[6] += qz * g10 - qx * g12;
+          acc[7] += qx * g11 - qy * g10;
+          acc[8] += g10; acc[9] += g11; acc[10] += g12;
+          acc[11] += qx * g21 - qy * g20;
+          acc[12] += g20; acc[13] += g21; acc[14] += g22;
+          acc[15] += mxx; acc[16] += mxy; acc[17] += mxz; acc[18] += myy; acc[19] += myz; acc[20] += mzz;
+          // b_t = [q x w ; w]
+          acc[21] += qy * wz - qz * wy;
+          acc[22] += qz * wx - qx * wz;
+          acc[23] += qx * wy - qy * wx;
+          acc[24] += wx; acc[25] += wy; acc[26] += wz;
+        }
+      }
+      __syncwarp();  // the queue is overwritten by the next round
     }
 
-    // ---------------- tile reduction ----------------
+    // ---------------- item reduction: warp -> 29 fp64 atomics ----------------
     if (MODE == GB_MODE_LINEARIZE) {
       const float r = warp_reduce_scatter32(acc, lane);
-      s_red[warp][lane] = r;
+      if (lane < 29) atomicAdd(&accum[(size_t)f * GB_ACC_STRIDE + lane], (double)r);
     } else {
       float e = acc[27], n = acc[28];
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) { e += __shfl_xor_sync(0xffffffffu, e, o); n += __shfl_xor_sync(0xffffffffu, n, o); }
-      if (lane == 0) { s_red[warp][27] = e; s_red[warp][28] = n; }
+      if (lane == 27) atomicAdd(&accum[(size_t)f * GB_ACC_STRIDE + 27], (double)e);
+      if (lane == 28) atomicAdd(&accum[(size_t)f * GB_ACC_STRIDE + 28], (double)n);
     }
-    __syncthreads();
-    if (warp == 0) {
-      const bool mine = (MODE == GB_MODE_LINEARIZE) ? (lane < 29) : (lane == 27 || lane == 28);
-      if (mine) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarps; w++) s += (double)s_red[w][lane];
-        atomicAdd(&accum[(size_t)f * GB_ACC_STRIDE + lane], s);
-      }
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) {
+      const unsigned ticket = atomicAdd(&done[f], 1u);
+      last = (ticket == (unsigned)D.num_tiles - 1u);
+      if (last) done[f] = 0u;  // self-cleaning
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
       __threadfence();
+      factor_epilogue(f, D, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, out, slab, reinterpret_cast<double*>(q));
       __syncwarp();
-      if (lane == 0) {
-        const unsigned ticket = atomicAdd(&done[f], 1u);
-        s_last = (ticket == (unsigned)D.num_tiles - 1u);
-        if (s_last) done[f] = 0u;  // self-cleaning
-        s_tile = next_tile;
-      }
-      __syncwarp();
-      if (s_last) {
-        __threadfence();
-        factor_epilogue(f, D, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, out, slab, s_epi);
-      }
     }
-    __syncthreads();
-    tile = s_tile;
+    item = __shfl_sync(0xffffffffu, next_item, 0);
   }
 }
 
@@ -377,12 +371,12 @@ gb_status gb_launch_sweep(gb_sweep* s, int mode) {
   if (s->num_tiles == 0) return GB_OK;
   gb_ctx* ctx = s->ctx;
   if (mode == GB_MODE_LINEARIZE)
-    k_vgicp_sweep<GB_MODE_LINEARIZE><<<s->grid, kThreads, 0, ctx->stream>>>(s->d_descs, s->d_poses, nullptr, s->d_tiles, s->num_tiles, s->tile_size / kWarps, s->d_tile_ctr, s->ctr_base, s->d_accum, s->d_done, s->d_out, s->d_slab);
+    k_vgicp_sweep<GB_MODE_LINEARIZE><<<s->grid, kThreads, 0, ctx->stream>>>(s->d_descs, s->d_poses, nullptr, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->d_done, s->d_out, s->d_slab);
   else
-    k_vgicp_sweep<GB_MODE_ERROR><<<s->grid, kThreads, 0, ctx->stream>>>(s->d_descs, s->d_poses, s->d_poses_eval, s->d_tiles, s->num_tiles, s->tile_size / kWarps, s->d_tile_ctr, s->ctr_base, s->d_accum, s->d_done, s->d_out, nullptr);
+    k_vgicp_sweep<GB_MODE_ERROR><<<s->grid, kThreads, 0, ctx->stream>>>(s->d_descs, s->d_poses, s->d_poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->d_done, s->d_out, nullptr);
   GB_CUDA(cudaGetLastError());
-  // every CTA draws tickets until it gets one past the end: the counter advances by num_tiles + grid per launch
-  s->ctr_base += (unsigned long long)s->num_tiles + (unsigned long long)s->grid;
+  // every warp draws tickets until it gets one past the end: the counter advances by num_items + warps per launch
+  s->ctr_base += (unsigned long long)s->num_tiles + (unsigned long long)s->grid * kWarps;
   ctx->launches++;
   return GB_OK;
 }

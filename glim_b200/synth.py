@@ -99,15 +99,22 @@ def make_hall_scene(seed_key=0) -> Scene:
     r = rng_for(1000, seed_key)
     gz = -1.8
     room = np.array([[-40.0, -25.0, gz], [40.0, 25.0, gz + 12.0]])
+    def clear_of_path(cx, cy, half):
+        # keep a 3 m corridor around the sensor path of arc_trajectory (radius 40 m about (0, -45)) free of obstacles
+        return abs(math.hypot(cx, cy + 45.0) - 40.0) > half + 3.0
+
     boxes = []
-    for _ in range(24):
+    while len(boxes) < 24:
         c = np.array([r.uniform(-36, 36), r.uniform(-22, 22)])
         s = r.uniform(0.8, 4.0, 2)
         h = r.uniform(0.8, 6.0)
-        boxes.append([[c[0] - s[0], c[1] - s[1], gz], [c[0] + s[0], c[1] + s[1], gz + h]])
+        if clear_of_path(c[0], c[1], float(np.hypot(s[0], s[1]))):
+            boxes.append([[c[0] - s[0], c[1] - s[1], gz], [c[0] + s[0], c[1] + s[1], gz + h]])
     cyl = []
-    for _ in range(12):
-        cyl.append([r.uniform(-36, 36), r.uniform(-22, 22), r.uniform(0.2, 0.8), gz, gz + r.uniform(3.0, 12.0)])
+    while len(cyl) < 12:
+        cx, cy, rad, top = r.uniform(-36, 36), r.uniform(-22, 22), r.uniform(0.2, 0.8), gz + r.uniform(3.0, 12.0)
+        if clear_of_path(cx, cy, rad):
+            cyl.append([cx, cy, rad, gz, top])
     return Scene(gz, room, np.array(boxes), np.array(cyl))
 
 
