@@ -321,14 +321,16 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     GB_REQUIRE(factors[f] && factors[f]->ctx == ctx, "factor belongs to another context");
     total_pts += factors[f]->source->n;
   }
-  const int ctas_per_sm = env_int("GB_CTAS_PER_SM", 2);
+  s->min_blocks = std::min(4, std::max(2, env_int("GB_MIN_BLOCKS", 2)));
+  const int ctas_per_sm = env_int("GB_CTAS_PER_SM", s->min_blocks);
   const int capacity = ctx->num_sms * ctas_per_sm;
   int tile = env_int("GB_TILE", 0);
   if (tile <= 0) {
     // work items are per WARP.  Small sweeps: one balanced item per warp (the per-item reduction is paid once);
     // large sweeps: 2048-point items handed out dynamically
+    // target ~6 items per warp (measured optimum on B200 across the five BASELINE workloads, profiles/tune_sweep_r01.txt)
     const uint64_t warps = (uint64_t)capacity * 8;
-    const uint64_t want = (total_pts + warps - 1) / warps;
+    const uint64_t want = total_pts / (warps * 6) + 1;
     tile = (int)std::min<uint64_t>(2048, std::max<uint64_t>(128, (want + 31) / 32 * 32));
   }
   tile = std::min(1 << 20, std::max(32, (tile + 31) / 32 * 32));

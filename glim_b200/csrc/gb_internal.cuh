@@ -111,7 +111,8 @@ struct gb_sweep {
   double* h_out;          // pinned
   float* d_slab;
   size_t num_pairs;
-  int num_tiles, tile_size, grid;
+  int num_tiles, tile_size, grid;   // work items, points per item, CTAs
+  int min_blocks;                   // kernel register-budget variant (CTAs per SM)
   uint64_t point_factors, algorithmic_bytes;
   uint64_t key;           // cache key
   uint64_t epoch;

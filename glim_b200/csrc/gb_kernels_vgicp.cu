@@ -190,8 +190,8 @@ __device__ __forceinline__ PoseF pose_from_colmajor(const double* __restrict__ T
   return P;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep(
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
   const FactorDesc* __restrict__ descs, const double* __restrict__ poses, const double* __restrict__ poses_eval,
   const int2* __restrict__ items, int num_items, int chunk,
   unsigned long long* __restrict__ item_ctr, unsigned long long ctr_base,
@@ -367,13 +367,25 @@ __global__ void __launch_bounds__(256) k_overlap(int num_targets, const FactorDe
 
 }  // namespace
 
+template <int MODE, int MINB>
+static void launch_variant(gb_sweep* s, const double* poses_eval, float* slab) {
+  k_vgicp_sweep<MODE, MINB><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->d_done, s->d_out, slab);
+}
+
 gb_status gb_launch_sweep(gb_sweep* s, int mode) {
   if (s->num_tiles == 0) return GB_OK;
   gb_ctx* ctx = s->ctx;
-  if (mode == GB_MODE_LINEARIZE)
-    k_vgicp_sweep<GB_MODE_LINEARIZE><<<s->grid, kThreads, 0, ctx->stream>>>(s->d_descs, s->d_poses, nullptr, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->d_done, s->d_out, s->d_slab);
-  else
-    k_vgicp_sweep<GB_MODE_ERROR><<<s->grid, kThreads, 0, ctx->stream>>>(s->d_descs, s->d_poses, s->d_poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->d_done, s->d_out, nullptr);
+  // register-budget variant: 2 CTAs/SM (124 regs, no spills), 3 (80 regs), 4 (64 regs); chosen when the sweep is created
+  const int v = s->min_blocks;
+  if (mode == GB_MODE_LINEARIZE) {
+    if (v >= 4) launch_variant<GB_MODE_LINEARIZE, 4>(s, nullptr, s->d_slab);
+    else if (v == 3) launch_variant<GB_MODE_LINEARIZE, 3>(s, nullptr, s->d_slab);
+    else launch_variant<GB_MODE_LINEARIZE, 2>(s, nullptr, s->d_slab);
+  } else {
+    if (v >= 4) launch_variant<GB_MODE_ERROR, 4>(s, s->d_poses_eval, nullptr);
+    else if (v == 3) launch_variant<GB_MODE_ERROR, 3>(s, s->d_poses_eval, nullptr);
+    else launch_variant<GB_MODE_ERROR, 2>(s, s->d_poses_eval, nullptr);
+  }
   GB_CUDA(cudaGetLastError());
   // every warp draws tickets until it gets one past the end: the counter advances by num_items + warps per launch
   s->ctr_base += (unsigned long long)s->num_tiles + (unsigned long long)s->grid * kWarps;
