@@ -18,7 +18,8 @@
 //                        moves on -- the fixed point is exactly the table a sequential first-free-slot
 //                        insertion in ascending voxel id builds (Shun & Blelloch's phase-concurrent
 //                        deterministic hashing), including which voxels run out of probes (<= max_scan)
-//   6. host loop         doubles num_buckets while dropped points > drop_rate * N
+//   6. host loop         num_buckets = init doubled until >= 2 V (load factor <= 0.5), then doubled again while
+//                        dropped points > drop_rate * N
 #include "gb_internal.cuh"
 
 #include <cub/cub.cuh>
@@ -189,7 +190,7 @@ gb_status gb_voxelmap_build_impl(gb_ctx* ctx, const gb_cloud* cloud, float resol
 
   // hash table: double until the dropped-point rate is acceptable
   int nb = init_buckets;
-  while (nb < V) nb *= 2;
+  while (nb < 2 * V) nb *= 2;  // load factor <= 0.5: short probe chains (same rule as the oracle)
   for (;;) {
     GB_CUDA(cudaMalloc((void**)&m->buckets, sizeof(int4) * (size_t)nb));
     k_table_clear<<<(nb + 255) / 256, 256, 0, st>>>(nb, m->buckets);
