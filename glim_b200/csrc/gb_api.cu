@@ -143,7 +143,7 @@ extern "C" gb_status gb_cloud_upload(gb_ctx* ctx, size_t n, const double* xyzw, 
   gb_cloud* c = new (std::nothrow) gb_cloud();
   if (!c) return GB_ERR_INTERNAL;
   c->ctx = ctx; c->n = n; c->base = nullptr; c->bytes = 0;
-  c->p0 = nullptr; c->p1 = nullptr; c->p2 = nullptr; c->normals = nullptr;
+  c->p0 = nullptr; c->p1 = nullptr; c->p2 = nullptr; c->normals = nullptr; c->perm = nullptr; c->inv_perm = nullptr;
   if (n == 0) { *out = c; return GB_OK; }
   // the reference casts Vector4d / Matrix4d to float on the host before the copy; so do we,
   // straight into the device plane layout, staged through pinned memory
@@ -168,14 +168,33 @@ extern "C" gb_status gb_cloud_upload(gb_ctx* ctx, size_t n, const double* xyzw, 
     h2[i] = c22;
     if (normals4) h3[i] = make_float4((float)normals4[4 * i], (float)normals4[4 * i + 1], (float)normals4[4 * i + 2], 0.f);
   }
-  cudaError_t e = cudaMalloc(&c->base, total);
-  if (e != cudaSuccess) { delete c; gb_set_error("cudaMalloc(%zu): %s", total, cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
-  c->bytes = total;
+  static const bool reorder = !(getenv("GB_NO_REORDER") && atoi(getenv("GB_NO_REORDER")));
+  const size_t bperm = reorder ? align_up(sizeof(int) * n, 256) : 0;
+  cudaError_t e = cudaMalloc(&c->base, total + 2 * bperm);
+  if (e != cudaSuccess) { delete c; gb_set_error("cudaMalloc(%zu): %s", total + 2 * bperm, cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
+  c->bytes = total + 2 * bperm;
   char* d = (char*)c->base;
   c->p0 = (float4*)d; c->p1 = (float4*)(d + b0); c->p2 = (float*)(d + b0 + b1); c->normals = normals4 ? (float4*)(d + b0 + b1 + b2) : nullptr;
-  e = cudaMemcpyAsync(c->base, h, total, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the pinned staging buffer is reused by the next call
-  if (e != cudaSuccess) { cudaFree(c->base); delete c; gb_set_error("upload: %s", cudaGetErrorString(e)); return GB_ERR_CUDA; }
+  if (reorder) { c->perm = (int*)(d + total); c->inv_perm = (int*)(d + total + bperm); }
+  st = GB_OK;
+  if (reorder) {
+    // stage the planes in the caller's order in scratch, then Morton-sort them into place on the device
+    char* scratch = nullptr;
+    st = gb_ctx_scratch(ctx, gb_cloud_reorder_scratch_bytes(n, total), (void**)&scratch);
+    if (st == GB_OK) {
+      e = cudaMemcpyAsync(scratch, h, total, cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) { gb_set_error("upload: %s", cudaGetErrorString(e)); st = GB_ERR_CUDA; }
+    }
+    if (st == GB_OK) st = gb_cloud_reorder_impl(ctx, c, scratch, b0, b1, b2, b3);
+  } else {
+    e = cudaMemcpyAsync(c->base, h, total, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { gb_set_error("upload: %s", cudaGetErrorString(e)); st = GB_ERR_CUDA; }
+  }
+  if (st == GB_OK) {
+    e = cudaStreamSynchronize(ctx->stream);  // the pinned staging buffer is reused by the next call
+    if (e != cudaSuccess) { gb_set_error("upload: %s", cudaGetErrorString(e)); st = GB_ERR_CUDA; }
+  }
+  if (st != GB_OK) { cudaFree(c->base); delete c; return st; }
   *out = c;
   return GB_OK;
 }
@@ -193,9 +212,12 @@ extern "C" gb_status gb_cloud_download(const gb_cloud* c, float* xyz, float* cov
   GB_CUDA(cudaMemcpy(h0.data(), c->p0, sizeof(float4) * c->n, cudaMemcpyDeviceToHost));
   GB_CUDA(cudaMemcpy(h1.data(), c->p1, sizeof(float4) * c->n, cudaMemcpyDeviceToHost));
   GB_CUDA(cudaMemcpy(h2.data(), c->p2, sizeof(float) * c->n, cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i < c->n; i++) {
-    if (xyz) { xyz[3 * i] = h0[i].x; xyz[3 * i + 1] = h0[i].y; xyz[3 * i + 2] = h0[i].z; }
-    if (cov6) { cov6[6 * i] = h0[i].w; cov6[6 * i + 1] = h1[i].x; cov6[6 * i + 2] = h1[i].y; cov6[6 * i + 3] = h1[i].z; cov6[6 * i + 4] = h1[i].w; cov6[6 * i + 5] = h2[i]; }
+  std::vector<int> perm;
+  if (c->perm) { perm.resize(c->n); GB_CUDA(cudaMemcpy(perm.data(), c->perm, sizeof(int) * c->n, cudaMemcpyDeviceToHost)); }
+  for (size_t j = 0; j < c->n; j++) {
+    const size_t i = c->perm ? (size_t)perm[j] : j;  // stored slot j holds the caller's point i
+    if (xyz) { xyz[3 * i] = h0[j].x; xyz[3 * i + 1] = h0[j].y; xyz[3 * i + 2] = h0[j].z; }
+    if (cov6) { cov6[6 * i] = h0[j].w; cov6[6 * i + 1] = h1[j].x; cov6[6 * i + 2] = h1[j].y; cov6[6 * i + 3] = h1[j].z; cov6[6 * i + 4] = h1[j].w; cov6[6 * i + 5] = h2[j]; }
   }
   return GB_OK;
 }

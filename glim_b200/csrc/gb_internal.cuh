@@ -47,6 +47,10 @@ struct gb_cloud {
   float4* p1;
   float* p2;
   float4* normals;  // {nx, ny, nz, 0} or nullptr
+  // Points are stored in Morton order of their 1/16 m cell (gather locality of the sweep kernel: lanes of a warp
+  // then hit the same few voxels).  perm[j] = original index of stored point j, inv_perm = its inverse; nullptr = identity.
+  int* perm;
+  int* inv_perm;
   void* base;       // one allocation
   size_t bytes;
 };
@@ -140,6 +144,8 @@ gb_status gb_ctx_pinned(gb_ctx* ctx, size_t bytes, void** out);   // pinned host
 enum { GB_MODE_LINEARIZE = 0, GB_MODE_ERROR = 1 };
 gb_status gb_launch_sweep(gb_sweep* s, int mode);
 gb_status gb_launch_overlap(gb_ctx* ctx, int num_targets, const FactorDesc* d_descs, const double* d_poses, int n, int* d_count);
+gb_status gb_cloud_reorder_impl(gb_ctx* ctx, gb_cloud* c, const void* staged /* device copy of the planes in original order */, size_t b0, size_t b1, size_t b2, size_t b3);
+size_t gb_cloud_reorder_scratch_bytes(size_t n, size_t staged_bytes);
 gb_status gb_voxelmap_build_impl(gb_ctx* ctx, const gb_cloud* cloud, float resolution, int init_buckets, int max_scan, double drop_rate, gb_voxelmap* out);
 gb_status gb_covariances_impl(gb_ctx* ctx, size_t n, const double* xyzw, const int32_t* neighbors, int kc, int k, double* normals4, double* cov4x4);
 gb_status gb_find_neighbors_impl(gb_ctx* ctx, size_t n, const double* xyzw, int k, int32_t* neighbors);

@@ -29,10 +29,12 @@ namespace {
 constexpr unsigned long long kInvalidKey = ~0ull;
 constexpr int kEmpty = 0x7fffffff;
 
-__global__ void k_point_keys(int n, const float4* __restrict__ p0, float inv_res, unsigned long long* __restrict__ keys, int* __restrict__ idx) {
+// i runs over ORIGINAL point indices (so that voxel sums are accumulated in the caller's point order, like the oracle);
+// inv_perm maps them to the Morton-ordered storage
+__global__ void k_point_keys(int n, const float4* __restrict__ p0, const int* __restrict__ inv_perm, float inv_res, unsigned long long* __restrict__ keys, int* __restrict__ idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float4 a = __ldg(&p0[i]);
+  const float4 a = __ldg(&p0[inv_perm ? inv_perm[i] : i]);
   unsigned long long key = kInvalidKey;
   if (isfinite(a.x) && isfinite(a.y) && isfinite(a.z)) {
     unsigned long long k;
@@ -60,14 +62,14 @@ __global__ void k_voxel_starts(int n, const unsigned long long* __restrict__ key
 }
 
 __global__ void k_voxel_reduce(int V, const int* __restrict__ starts, const unsigned long long* __restrict__ keys, const int* __restrict__ idx,
-                               const float4* __restrict__ p0, const float4* __restrict__ p1, const float* __restrict__ p2,
+                               const float4* __restrict__ p0, const float4* __restrict__ p1, const float* __restrict__ p2, const int* __restrict__ inv_perm,
                                float4* __restrict__ voxels, int4* __restrict__ vcoord) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
   const int b = starts[v], e = starts[v + 1];
   float sx = 0.f, sy = 0.f, sz = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f;
   for (int s = b; s < e; s++) {
-    const int i = idx[s];
+    const int i = inv_perm ? inv_perm[idx[s]] : idx[s];
     const float4 a0 = __ldg(&p0[i]);
     const float4 a1 = __ldg(&p1[i]);
     const float a2 = __ldg(&p2[i]);
@@ -168,7 +170,7 @@ gb_status gb_voxelmap_build_impl(gb_ctx* ctx, const gb_cloud* cloud, float resol
     d_dropped = (int*)p;
 
     const int tb = 256, gb = (n + tb - 1) / tb;
-    k_point_keys<<<gb, tb, 0, st>>>(n, cloud->p0, m->inv_res, d_keys, d_idx);
+    k_point_keys<<<gb, tb, 0, st>>>(n, cloud->p0, cloud->inv_perm, m->inv_res, d_keys, d_idx);
     size_t tmp = cub_bytes;
     GB_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, tmp, d_keys, d_keys_s, d_idx, d_idx_s, n, 0, 64, st));
     k_head_flags<<<gb, tb, 0, st>>>(n, d_keys_s, d_flags);
@@ -181,7 +183,7 @@ gb_status gb_voxelmap_build_impl(gb_ctx* ctx, const gb_cloud* cloud, float resol
       GB_CUDA(cudaMalloc(&m->base, sizeof(float4) * 3 * (size_t)V));
       m->voxels = (float4*)m->base;
       k_voxel_starts<<<gb, tb, 0, st>>>(n, d_keys_s, d_flags, d_pos, d_starts);
-      k_voxel_reduce<<<(V + 127) / 128, 128, 0, st>>>(V, d_starts, d_keys_s, d_idx_s, cloud->p0, cloud->p1, cloud->p2, m->voxels, d_vcoord);
+      k_voxel_reduce<<<(V + 127) / 128, 128, 0, st>>>(V, d_starts, d_keys_s, d_idx_s, cloud->p0, cloud->p1, cloud->p2, cloud->inv_perm, m->voxels, d_vcoord);
       ctx->launches += 2;
     }
   }
@@ -217,4 +219,81 @@ gb_status gb_voxelmap_build_impl(gb_ctx* ctx, const gb_cloud* cloud, float resol
   }
   m->bytes += sizeof(int4) * (size_t)m->num_buckets;
   return GB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Morton reordering of a freshly uploaded cloud (PointCloudGPU::clone keeps the caller's order on the host side of the
+// boundary: gb_cloud_download and the voxel-map sums un-permute; only the device storage order changes).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ unsigned long long spread21(unsigned long long v) {  // 21 bits -> every third bit
+  v &= 0x1FFFFFull;
+  v = (v | (v << 32)) & 0x1F00000000FFFFull;
+  v = (v | (v << 16)) & 0x1F0000FF0000FFull;
+  v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+  v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+  v = (v | (v << 2)) & 0x1249249249249249ull;
+  return v;
+}
+__global__ void k_morton_keys(int n, const float4* __restrict__ p0, unsigned long long* __restrict__ keys, int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = p0[i];
+  unsigned long long key = ~0ull;  // non-finite / far-away points go last
+  if (isfinite(a.x) && isfinite(a.y) && isfinite(a.z)) {
+    const float s = 16.0f;  // 1/16 m cells
+    const float fx = floorf(a.x * s), fy = floorf(a.y * s), fz = floorf(a.z * s);
+    if (fabsf(fx) < 1048576.f && fabsf(fy) < 1048576.f && fabsf(fz) < 1048576.f) {
+      const unsigned long long x = (unsigned long long)((int)fx + (1 << 20)), y = (unsigned long long)((int)fy + (1 << 20)), z = (unsigned long long)((int)fz + (1 << 20));
+      key = (spread21(x) << 2) | (spread21(y) << 1) | spread21(z);
+    }
+  }
+  keys[i] = key;
+  idx[i] = i;
+}
+__global__ void k_permute_cloud(int n, const int* __restrict__ perm, const float4* __restrict__ s0, const float4* __restrict__ s1, const float* __restrict__ s2, const float4* __restrict__ s3,
+                                float4* __restrict__ d0, float4* __restrict__ d1, float* __restrict__ d2, float4* __restrict__ d3, int* __restrict__ inv_perm) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int i = perm[j];
+  d0[j] = s0[i];
+  d1[j] = s1[i];
+  d2[j] = s2[i];
+  if (s3) d3[j] = s3[i];
+  inv_perm[i] = j;
+}
+}  // namespace
+
+gb_status gb_cloud_reorder_impl(gb_ctx* ctx, gb_cloud* c, const void* staged, size_t b0, size_t b1, size_t b2, size_t b3) {
+  const int n = (int)c->n;
+  cudaStream_t st = ctx->stream;
+  const char* sp = (const char*)staged;
+  const float4* s0 = (const float4*)sp;
+  const float4* s1 = (const float4*)(sp + b0);
+  const float* s2 = (const float*)(sp + b0 + b1);
+  const float4* s3 = b3 ? (const float4*)(sp + b0 + b1 + b2) : nullptr;
+  size_t cub_sort = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_sort, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, n, 0, 64, st);
+  const size_t cub_b = align_up(cub_sort, 256), key_b = align_up(sizeof(unsigned long long) * (size_t)n, 256), idx_b = align_up(sizeof(int) * (size_t)n, 256);
+  // the staged planes live at the start of the ctx scratch buffer; our temporaries go behind them (the caller sized it)
+  char* p = (char*)staged + align_up(b0 + b1 + b2 + b3, 256);
+  void* d_cub = p; p += cub_b;
+  unsigned long long* d_keys = (unsigned long long*)p; p += key_b;
+  unsigned long long* d_keys_s = (unsigned long long*)p; p += key_b;
+  int* d_idx = (int*)p; p += idx_b;
+  const int tb = 256, gb = (n + tb - 1) / tb;
+  k_morton_keys<<<gb, tb, 0, st>>>(n, s0, d_keys, d_idx);
+  size_t tmp = cub_b;
+  GB_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, tmp, d_keys, d_keys_s, d_idx, c->perm, n, 0, 64, st));
+  k_permute_cloud<<<gb, tb, 0, st>>>(n, c->perm, s0, s1, s2, s3, c->p0, c->p1, c->p2, c->normals, c->inv_perm);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches += 3;
+  return GB_OK;
+}
+
+size_t gb_cloud_reorder_scratch_bytes(size_t n, size_t staged_bytes) {
+  size_t cub_sort = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_sort, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, (int)n, 0, 64, (cudaStream_t)0);
+  return align_up(staged_bytes, 256) + align_up(cub_sort, 256) + 2 * align_up(sizeof(unsigned long long) * n, 256) + align_up(sizeof(int) * n, 256) + 256;
 }
