@@ -411,6 +411,10 @@ def main():
     ems, _, _ = timed(step_e2e, e_steps, False)
     e2e_val = total_pf / (ems / e_steps * 1e-3) / 1e6
 
+    # checksum of the (all-reduced) Hessian slab of one step: identical at every N up to fp32 reduction order
+    step_device()
+    torch.cuda.synchronize()
+    slab_checksum = float(sum(s.double().abs().sum().item() for s in slabs))
     if sampler:
         time.sleep(0.15)
         sampler.stop()
@@ -425,6 +429,7 @@ def main():
             "gpu_launches": int(gpu_launches),
             "clocks": sampler.summary(t0, t1) if sampler else None,
             "roofline": roofline,
+            "slab_checksum": slab_checksum,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w, args.cpu_seconds)
