@@ -1,0 +1,495 @@
+// gtsam_points_compat.hpp -- header-only C++17 shims that give libglim_b200.so the class surface GLIM's modules
+// construct from gtsam_points (SURVEY.md 8(b) "inner boundary").  Same names, constructor arguments, defaults
+// and call order as the reference call sites; every method forwards to the C-ABI of include/glim_b200.h.
+//
+//   gtsam_points::CUDAStream / StreamTempBufferRoundRobin     src/glim/odometry/odometry_estimation_gpu.cpp:76-77, :139-141
+//   gtsam_points::PointCloudGPU::clone(frame[, stream])      src/glim/odometry/odometry_estimation_gpu.cpp:96; src/glim/mapping/sub_mapping.cpp:168
+//   gtsam_points::GaussianVoxelMapGPU(res, 8192*2, 10, 1e-3, stream)::insert(frame)   odometry_estimation_gpu.cpp:103-104
+//   gtsam_points::IntegratedVGICPFactorGPU(key | pose, key, voxelmap, frame, stream, buffer)   odometry_estimation_gpu.cpp:144, :161
+//   gtsam_points::NonlinearFactorSetGPU::add / linearize    odometry_estimation_gpu.cpp:383-386
+//   gtsam_points::overlap_gpu / overlap_auto                 odometry_estimation_gpu.cpp:231, :248; src/glim/mapping/global_mapping.cpp:448
+//   gtsam_points::median_distance                            odometry_estimation_gpu.cpp:91
+//
+// Two build modes:
+//   * default: self-contained.  Poses are `Pose` (16 doubles, column-major == Eigen::Isometry3d::data()), keys are
+//     uint64_t, `Values` is std::map<Key, Pose>, and linearize() returns the raw gb_linearized6 blocks.  This is
+//     what tests/cpp/ compiles and runs here (GTSAM / Eigen are not installed in this environment).
+//   * -DGLIM_B200_WITH_GTSAM: IntegratedVGICPFactorGPU derives from gtsam::NonlinearFactor, takes gtsam::Key /
+//     gtsam::Pose3 / gtsam::Values and returns gtsam::HessianFactor exactly as the reference factor does
+//     (SURVEY A.3).  Compile-checked only against the signature stubs of tests/cpp/gtsam_stub.
+#pragma once
+
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../glim_b200.h"
+
+#ifdef GLIM_B200_WITH_GTSAM
+#include <gtsam/geometry/Pose3.h>
+#include <gtsam/linear/HessianFactor.h>
+#include <gtsam/nonlinear/NonlinearFactor.h>
+#include <gtsam/nonlinear/NonlinearFactorGraph.h>
+#include <gtsam/nonlinear/Values.h>
+#endif
+
+struct CUstream_st;  // the reference passes raw CUDA stream handles around
+
+// whether gtsam_points' evaluate() carries a 1/2 in `error` is version dependent; the C-ABI returns
+// the raw sum r^T M r and the shim applies this compile-time scale.
+#ifndef GLIM_B200_ERROR_SCALE
+#define GLIM_B200_ERROR_SCALE 1.0
+#endif
+
+namespace glim_b200 {
+
+inline void check(gb_status st, const char* what) {
+  if (st != GB_OK) throw std::runtime_error(std::string(what) + ": " + gb_status_string(st) + ": " + gb_last_error());
+}
+
+/// 4x4 rigid transform, 16 doubles column-major (bit-compatible with Eigen::Isometry3d::data()).
+struct Pose {
+  std::array<double, 16> m{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}};
+  const double* data() const { return m.data(); }
+  double& operator()(int r, int c) { return m[c * 4 + r]; }
+  double operator()(int r, int c) const { return m[c * 4 + r]; }
+  Pose inverse() const {
+    Pose o;
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) o(r, c) = (*this)(c, r);
+      o(r, 3) = -((*this)(0, r) * (*this)(0, 3) + (*this)(1, r) * (*this)(1, 3) + (*this)(2, r) * (*this)(2, 3));
+    }
+    return o;
+  }
+  Pose operator*(const Pose& b) const {
+    Pose o;
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) {
+        double s = 0;
+        for (int k = 0; k < 4; k++) s += (*this)(r, k) * b(k, c);
+        o(r, c) = s;
+      }
+    return o;
+  }
+};
+
+/// One gb_ctx per thread of execution (the reference drives each module from one executor thread).
+class Context {
+public:
+  explicit Context(int device = 0) { check(gb_ctx_create(device, &ctx_), "gb_ctx_create"); }
+  Context(int device, CUstream_st* stream) { check(gb_ctx_create_on_stream(device, stream, &ctx_), "gb_ctx_create_on_stream"); }
+  ~Context() { gb_ctx_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  gb_ctx* get() const { return ctx_; }
+  static std::shared_ptr<Context> default_context() {
+    static thread_local std::shared_ptr<Context> c = std::make_shared<Context>(0);
+    return c;
+  }
+
+private:
+  gb_ctx* ctx_ = nullptr;
+};
+
+}  // namespace glim_b200
+
+namespace gtsam_points {
+
+#ifdef GLIM_B200_WITH_GTSAM
+using Key = gtsam::Key;
+using Values = gtsam::Values;
+#else
+using Key = std::uint64_t;
+using Values = std::map<Key, glim_b200::Pose>;
+#endif
+
+/// gtsam_points::CUDAStream: owns the context (stream) the frame's GPU work is ordered on.
+class CUDAStream {
+public:
+  CUDAStream() : ctx_(std::make_shared<glim_b200::Context>(0)) {}
+  operator CUstream_st*() const { return static_cast<CUstream_st*>(gb_ctx_stream(ctx_->get())); }
+  const std::shared_ptr<glim_b200::Context>& context() const { return ctx_; }
+
+private:
+  std::shared_ptr<glim_b200::Context> ctx_;
+};
+
+/// gtsam_points::TempBufferManager: scratch is owned by the gb_ctx arena, the handle only keeps it alive.
+class TempBufferManager {
+public:
+  explicit TempBufferManager(std::shared_ptr<glim_b200::Context> ctx) : ctx(std::move(ctx)) {}
+  std::shared_ptr<glim_b200::Context> ctx;
+};
+
+/// gtsam_points::StreamTempBufferRoundRobin(N): the reference hands out N (stream, buffer) pairs so that N factors
+/// can run concurrently.  The fused sweep runs all factors of a graph in ONE launch, so every pair maps to the
+/// same context; N is accepted and ignored.
+class StreamTempBufferRoundRobin {
+public:
+  explicit StreamTempBufferRoundRobin(int /*num_streams*/ = 8) : ctx_(std::make_shared<glim_b200::Context>(0)), buffer_(std::make_shared<TempBufferManager>(ctx_)) {}
+  std::pair<CUstream_st*, std::shared_ptr<TempBufferManager>> get_stream_buffer() { return {static_cast<CUstream_st*>(gb_ctx_stream(ctx_->get())), buffer_}; }
+  const std::shared_ptr<glim_b200::Context>& context() const { return ctx_; }
+
+private:
+  std::shared_ptr<glim_b200::Context> ctx_;
+  std::shared_ptr<TempBufferManager> buffer_;
+};
+
+/// gtsam_points::PointCloud (host view: the members GLIM reads, include/glim/odometry/estimation_frame.hpp:103).
+struct PointCloud {
+  using Ptr = std::shared_ptr<PointCloud>;
+  using ConstPtr = std::shared_ptr<const PointCloud>;
+  virtual ~PointCloud() = default;
+  std::size_t size() const { return num_points; }
+  bool has_points() const { return points != nullptr; }
+  bool has_covs() const { return covs != nullptr; }
+  bool has_normals() const { return normals != nullptr; }
+  std::size_t num_points = 0;
+  const double* points = nullptr;   // N x Vector4d
+  const double* covs = nullptr;     // N x Matrix4d, column-major
+  const double* normals = nullptr;  // N x Vector4d
+};
+
+/// gtsam_points::PointCloudGPU: device copy (fp32) of a PointCloud.
+class PointCloudGPU : public PointCloud {
+public:
+  using Ptr = std::shared_ptr<PointCloudGPU>;
+  using ConstPtr = std::shared_ptr<const PointCloudGPU>;
+  ~PointCloudGPU() override { gb_cloud_destroy(cloud_); }
+
+  static Ptr clone(const PointCloud& frame, const std::shared_ptr<glim_b200::Context>& ctx = glim_b200::Context::default_context()) {
+    Ptr c(new PointCloudGPU);
+    c->ctx_ = ctx;
+    c->num_points = frame.num_points;
+    c->points = frame.points;
+    c->covs = frame.covs;
+    c->normals = frame.normals;
+    glim_b200::check(gb_cloud_upload(ctx->get(), frame.num_points, frame.points, frame.covs, frame.normals, &c->cloud_), "gb_cloud_upload");
+    return c;
+  }
+  static Ptr clone(const PointCloud& frame, const CUDAStream& stream) { return clone(frame, stream.context()); }
+  bool has_points_gpu() const { return cloud_ != nullptr; }
+  bool has_covs_gpu() const { return cloud_ != nullptr && covs != nullptr; }
+  gb_cloud* handle() const { return cloud_; }
+  const std::shared_ptr<glim_b200::Context>& context() const { return ctx_; }
+
+private:
+  PointCloudGPU() = default;
+  std::shared_ptr<glim_b200::Context> ctx_;
+  gb_cloud* cloud_ = nullptr;
+};
+
+struct VoxelMapInfo {
+  int num_voxels = 0;
+  int num_buckets = 0;
+  int max_bucket_scan_count = 0;
+  float voxel_resolution = 0.f;
+};
+
+struct GaussianVoxelMap {
+  using Ptr = std::shared_ptr<GaussianVoxelMap>;
+  using ConstPtr = std::shared_ptr<const GaussianVoxelMap>;
+  virtual ~GaussianVoxelMap() = default;
+  virtual double voxel_resolution() const = 0;
+};
+
+/// gtsam_points::GaussianVoxelMapGPU(resolution, init_num_buckets, max_bucket_scan_count, target_points_drop_rate, stream)
+class GaussianVoxelMapGPU : public GaussianVoxelMap {
+public:
+  using Ptr = std::shared_ptr<GaussianVoxelMapGPU>;
+  using ConstPtr = std::shared_ptr<const GaussianVoxelMapGPU>;
+  explicit GaussianVoxelMapGPU(float resolution, int init_num_buckets = 8192 * 2, int max_bucket_scan_count = 10, double target_points_drop_rate = 1e-3, CUstream_st* /*stream*/ = nullptr)
+  : resolution_(resolution), init_num_buckets_(init_num_buckets), max_bucket_scan_count_(max_bucket_scan_count), target_points_drop_rate_(target_points_drop_rate) {}
+  ~GaussianVoxelMapGPU() override { gb_voxelmap_destroy(map_); }
+
+  /// insert(frame): `frame` must be (or is uploaded as) a PointCloudGPU; one insert per map, as at every GLIM call site.
+  void insert(const PointCloud& frame) {
+    if (map_) throw std::runtime_error("GaussianVoxelMapGPU::insert called twice");
+    const auto* gpu = dynamic_cast<const PointCloudGPU*>(&frame);
+    PointCloudGPU::Ptr tmp;
+    if (!gpu) { tmp = PointCloudGPU::clone(frame); gpu = tmp.get(); }
+    ctx_ = gpu->context();
+    glim_b200::check(gb_voxelmap_build(ctx_->get(), gpu->handle(), resolution_, init_num_buckets_, max_bucket_scan_count_, target_points_drop_rate_, &map_), "gb_voxelmap_build");
+    float r = 0.f;
+    gb_voxelmap_info(map_, &voxelmap_info.num_voxels, &voxelmap_info.num_buckets, &r);
+    voxelmap_info.voxel_resolution = r;
+    voxelmap_info.max_bucket_scan_count = max_bucket_scan_count_;
+  }
+  double voxel_resolution() const override { return resolution_; }
+  gb_voxelmap* handle() const { return map_; }
+  const std::shared_ptr<glim_b200::Context>& context() const { return ctx_; }
+  VoxelMapInfo voxelmap_info;
+
+private:
+  float resolution_;
+  int init_num_buckets_, max_bucket_scan_count_;
+  double target_points_drop_rate_;
+  std::shared_ptr<glim_b200::Context> ctx_;
+  gb_voxelmap* map_ = nullptr;
+};
+
+/// Result of one linearization in the default (GTSAM-free) build.
+struct LinearizedSystem6 {
+  gb_linearized6 blocks;  // H_tt H_ss H_ts b_t b_s error num_inliers (column-major 6x6, [rot; trans])
+  bool binary;
+};
+
+/// gtsam_points::IntegratedVGICPFactorGPU
+class IntegratedVGICPFactorGPU
+#ifdef GLIM_B200_WITH_GTSAM
+: public gtsam::NonlinearFactor
+#endif
+{
+public:
+  using shared_ptr = std::shared_ptr<IntegratedVGICPFactorGPU>;
+
+  /// binary: (target_key, source_key, target voxelmap, source frame, stream, buffer)   odometry_estimation_gpu.cpp:144
+  IntegratedVGICPFactorGPU(Key target_key, Key source_key, const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, CUstream_st* = nullptr, std::shared_ptr<TempBufferManager> = nullptr)
+#ifdef GLIM_B200_WITH_GTSAM
+  : gtsam::NonlinearFactor(gtsam::KeyVector{target_key, source_key}),
+#else
+  :
+#endif
+    is_binary_(true), target_key_(target_key), source_key_(source_key) {
+    init(target, source);
+  }
+  /// unary: (fixed_target_pose, source_key, ...)   odometry_estimation_gpu.cpp:161
+#ifdef GLIM_B200_WITH_GTSAM
+  IntegratedVGICPFactorGPU(const gtsam::Pose3& fixed_target_pose, Key source_key, const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, CUstream_st* = nullptr, std::shared_ptr<TempBufferManager> = nullptr)
+  : gtsam::NonlinearFactor(gtsam::KeyVector{source_key}), is_binary_(false), target_key_(0), source_key_(source_key) {
+    const gtsam::Matrix4 M = fixed_target_pose.matrix();
+    for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) fixed_target_pose_(r, c) = M(r, c);
+    init(target, source);
+  }
+#else
+  IntegratedVGICPFactorGPU(const glim_b200::Pose& fixed_target_pose, Key source_key, const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, CUstream_st* = nullptr, std::shared_ptr<TempBufferManager> = nullptr)
+  : is_binary_(false), target_key_(0), source_key_(source_key), fixed_target_pose_(fixed_target_pose) {
+    init(target, source);
+  }
+#endif
+  ~IntegratedVGICPFactorGPU() { gb_vgicp_factor_destroy(factor_); }
+  IntegratedVGICPFactorGPU(const IntegratedVGICPFactorGPU&) = delete;
+
+  /// set_enable_surface_validation(bool)   odometry_estimation_gpu.cpp:145
+  void set_enable_surface_validation(bool enable) {
+    if (enable != surface_validation_) {
+      surface_validation_ = enable;
+      recreate();
+    }
+  }
+  std::size_t dim() const
+#ifdef GLIM_B200_WITH_GTSAM
+    override
+#endif
+  { return 6; }
+  bool is_binary() const { return is_binary_; }
+  Key target_key() const { return target_key_; }
+  Key source_key() const { return source_key_; }
+  const glim_b200::Pose& get_fixed_target_pose() const { return fixed_target_pose_; }  // standard_viewer_callbacks.cpp:283
+  std::size_t memory_usage() const { return sizeof(*this); }                           // standard_viewer_mem.cpp:160
+  std::size_t memory_usage_gpu() const { return 122 * sizeof(double) + 64; }           // standard_viewer_mem.cpp:161
+  double inlier_fraction() const { return source_->size() ? last_num_inliers_ / static_cast<double>(source_->size()) : 0.0; }
+  gb_factor* handle() const { return factor_; }
+
+  /// delta = T_target^-1 * T_source
+  glim_b200::Pose delta(const Values& values) const {
+    const glim_b200::Pose Ts = pose_of(values, source_key_);
+    const glim_b200::Pose Tt = is_binary_ ? pose_of(values, target_key_) : fixed_target_pose_;
+    return Tt.inverse() * Ts;
+  }
+
+  /// raw linearization (GTSAM-free); the batched path stores its result through set_cached()
+  LinearizedSystem6 linearize_raw(const Values& values) {
+    const glim_b200::Pose d = delta(values);
+    LinearizedSystem6 out;
+    out.binary = is_binary_;
+    glim_b200::check(gb_vgicp_linearize(factor_, d.data(), &out.blocks), "gb_vgicp_linearize");
+    lin_point_ = d;
+    have_lin_point_ = true;
+    last_num_inliers_ = out.blocks.num_inliers;
+    return out;
+  }
+  /// error(values): inlier set of the last linearization point, evaluated at `values`
+  double error(const Values& values) const
+#ifdef GLIM_B200_WITH_GTSAM
+    override
+#endif
+  {
+    const glim_b200::Pose d = delta(values);
+    double e = 0.0;
+    glim_b200::check(gb_vgicp_error(factor_, have_lin_point_ ? lin_point_.data() : d.data(), d.data(), &e), "gb_vgicp_error");
+    return GLIM_B200_ERROR_SCALE * e;
+  }
+
+#ifdef GLIM_B200_WITH_GTSAM
+  /// linearize(values) -> gtsam::HessianFactor; uses the cached batch result when NonlinearFactorSetGPU ran
+  std::shared_ptr<gtsam::GaussianFactor> linearize(const gtsam::Values& values) const override {
+    auto* self = const_cast<IntegratedVGICPFactorGPU*>(this);
+    gb_linearized6 L;
+    if (self->cached_valid_) { L = self->cached_; self->cached_valid_ = false; } else { L = self->linearize_raw(values).blocks; }
+    gtsam::Matrix6 H_tt, H_ss, H_ts;
+    gtsam::Vector6 g_t, g_s;  // HessianFactor takes the NEGATED gradients
+    for (int c = 0; c < 6; c++) {
+      for (int r = 0; r < 6; r++) { H_tt(r, c) = L.H_tt[c * 6 + r]; H_ss(r, c) = L.H_ss[c * 6 + r]; H_ts(r, c) = L.H_ts[c * 6 + r]; }
+      g_t(c) = -L.b_t[c];
+      g_s(c) = -L.b_s[c];
+    }
+    if (is_binary_) return std::make_shared<gtsam::HessianFactor>(target_key_, source_key_, H_tt, H_ts, g_t, H_ss, g_s, GLIM_B200_ERROR_SCALE * L.error);
+    return std::make_shared<gtsam::HessianFactor>(source_key_, H_ss, g_s, GLIM_B200_ERROR_SCALE * L.error);
+  }
+  gtsam::NonlinearFactor::shared_ptr clone() const override {
+    std::shared_ptr<IntegratedVGICPFactorGPU> f;
+    if (is_binary_) {
+      f = std::make_shared<IntegratedVGICPFactorGPU>(target_key_, source_key_, target_, source_);
+    } else {
+      gtsam::Matrix4 M;
+      for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) M(r, c) = fixed_target_pose_(r, c);
+      f = std::make_shared<IntegratedVGICPFactorGPU>(gtsam::Pose3(M), source_key_, target_, source_);
+    }
+    f->set_enable_surface_validation(surface_validation_);
+    return f;
+  }
+#endif
+
+  // used by NonlinearFactorSetGPU
+  void set_cached(const gb_linearized6& L, const glim_b200::Pose& lin_point) {
+    cached_ = L; cached_valid_ = true; lin_point_ = lin_point; have_lin_point_ = true; last_num_inliers_ = L.num_inliers;
+  }
+  bool take_cached(gb_linearized6* out) { if (!cached_valid_) return false; *out = cached_; cached_valid_ = false; return true; }
+  const std::shared_ptr<glim_b200::Context>& context() const { return ctx_; }
+
+private:
+  static glim_b200::Pose pose_of(const Values& values, Key k) {
+#ifdef GLIM_B200_WITH_GTSAM
+    const gtsam::Matrix4 M = values.at<gtsam::Pose3>(k).matrix();
+    glim_b200::Pose p;
+    for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) p(r, c) = M(r, c);
+    return p;
+#else
+    return values.at(k);
+#endif
+  }
+  void init(const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source) {
+    target_ = std::dynamic_pointer_cast<const GaussianVoxelMapGPU>(target);
+    source_ = std::dynamic_pointer_cast<const PointCloudGPU>(source);
+    if (!target_ || !target_->handle()) throw std::runtime_error("IntegratedVGICPFactorGPU: target is not a (built) GaussianVoxelMapGPU");
+    if (!source_ || !source_->handle()) throw std::runtime_error("IntegratedVGICPFactorGPU: source has no GPU points (PointCloudGPU::clone it first)");
+    ctx_ = source_->context();
+    recreate();
+  }
+  void recreate() {
+    if (factor_) gb_vgicp_factor_destroy(factor_);
+    factor_ = nullptr;
+    glim_b200::check(gb_vgicp_factor_create(ctx_->get(), target_->handle(), source_->handle(), surface_validation_ ? GB_FACTOR_SURFACE_VALIDATION : 0, &factor_), "gb_vgicp_factor_create");
+  }
+
+  bool is_binary_;
+  Key target_key_, source_key_;
+  glim_b200::Pose fixed_target_pose_;
+  GaussianVoxelMapGPU::ConstPtr target_;  // kept alive, as the reference factor keeps shared_ptrs
+  PointCloudGPU::ConstPtr source_;
+  std::shared_ptr<glim_b200::Context> ctx_;
+  gb_factor* factor_ = nullptr;
+  bool surface_validation_ = false;
+  glim_b200::Pose lin_point_;
+  bool have_lin_point_ = false;
+  double last_num_inliers_ = 0.0;
+  gb_linearized6 cached_{};
+  bool cached_valid_ = false;
+};
+
+/// gtsam_points::NonlinearFactorSetGPU: add(graph) collects the GPU factors; linearize(values) runs ONE fused sweep
+/// (F x 128 B of poses down, F records up) and caches every factor's result for the GTSAM linearize() that follows
+/// (odometry_estimation_gpu.cpp:383-386).
+class NonlinearFactorSetGPU {
+public:
+  void clear() { factors_.clear(); }
+  std::size_t size() const { return factors_.size(); }
+  bool add(const std::shared_ptr<IntegratedVGICPFactorGPU>& f) {
+    if (!f) return false;
+    factors_.push_back(f);
+    return true;
+  }
+#ifdef GLIM_B200_WITH_GTSAM
+  void add(const gtsam::NonlinearFactorGraph& graph) {
+    for (const auto& f : graph) add(std::dynamic_pointer_cast<IntegratedVGICPFactorGPU>(f));
+  }
+#else
+  template <typename Container>
+  void add(const Container& graph) {
+    for (const auto& f : graph) add(f);
+  }
+#endif
+  void linearize(const Values& values) {
+    const std::size_t F = factors_.size();
+    if (!F) return;
+    std::vector<gb_factor*> handles(F);
+    std::vector<glim_b200::Pose> deltas(F);
+    std::vector<double> T(16 * F);
+    for (std::size_t i = 0; i < F; i++) {
+      handles[i] = factors_[i]->handle();
+      deltas[i] = factors_[i]->delta(values);
+      std::copy(deltas[i].m.begin(), deltas[i].m.end(), T.begin() + 16 * i);
+    }
+    results_.resize(F);
+    glim_b200::check(gb_factor_set_linearize(factors_[0]->context()->get(), F, handles.data(), T.data(), results_.data()), "gb_factor_set_linearize");
+    for (std::size_t i = 0; i < F; i++) factors_[i]->set_cached(results_[i], deltas[i]);
+  }
+  const std::vector<gb_linearized6>& results() const { return results_; }
+
+private:
+  std::vector<std::shared_ptr<IntegratedVGICPFactorGPU>> factors_;
+  std::vector<gb_linearized6> results_;
+};
+
+/// gtsam_points::overlap_gpu(voxelmap, source, delta, stream)   odometry_estimation_gpu.cpp:248
+inline double overlap_gpu(const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, const glim_b200::Pose& delta, CUstream_st* = nullptr) {
+  const auto t = std::dynamic_pointer_cast<const GaussianVoxelMapGPU>(target);
+  const auto s = std::dynamic_pointer_cast<const PointCloudGPU>(source);
+  if (!t || !s) throw std::runtime_error("overlap_gpu: GPU voxel map / GPU point cloud required");
+  const gb_voxelmap* maps[1] = {t->handle()};
+  double ov = 0.0;
+  glim_b200::check(gb_overlap(s->context()->get(), 1, maps, s->handle(), delta.data(), &ov), "gb_overlap");
+  return ov;
+}
+/// gtsam_points::overlap_gpu(voxelmaps, source, deltas, stream)   odometry_estimation_gpu.cpp:231
+inline double overlap_gpu(const std::vector<GaussianVoxelMap::ConstPtr>& targets, const PointCloud::ConstPtr& source, const std::vector<glim_b200::Pose>& deltas, CUstream_st* = nullptr) {
+  const auto s = std::dynamic_pointer_cast<const PointCloudGPU>(source);
+  if (!s || targets.size() != deltas.size()) throw std::runtime_error("overlap_gpu: bad arguments");
+  std::vector<const gb_voxelmap*> maps(targets.size());
+  std::vector<double> T(16 * targets.size());
+  for (std::size_t i = 0; i < targets.size(); i++) {
+    const auto t = std::dynamic_pointer_cast<const GaussianVoxelMapGPU>(targets[i]);
+    if (!t) throw std::runtime_error("overlap_gpu: GPU voxel map required");
+    maps[i] = t->handle();
+    std::copy(deltas[i].m.begin(), deltas[i].m.end(), T.begin() + 16 * i);
+  }
+  double ov = 0.0;
+  glim_b200::check(gb_overlap(s->context()->get(), maps.size(), maps.data(), s->handle(), T.data(), &ov), "gb_overlap");
+  return ov;
+}
+/// gtsam_points::overlap_auto: GPU voxel maps dispatch to overlap_gpu (sub_mapping.cpp:252; global_mapping.cpp:322, :448)
+inline double overlap_auto(const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, const glim_b200::Pose& delta) { return overlap_gpu(target, source, delta); }
+
+/// gtsam_points::median_distance(frame, max_scan_count)   odometry_estimation_gpu.cpp:91  (256 strided samples: host)
+inline double median_distance(const PointCloud::ConstPtr& frame, int max_scan_count) {
+  const std::size_t n = frame->size();
+  if (!n) return 0.0;
+  const std::size_t step = std::max<std::size_t>(1, n / static_cast<std::size_t>(max_scan_count));
+  std::vector<double> d;
+  for (std::size_t i = 0; i < n; i += step) {
+    const double* p = frame->points + 4 * i;
+    d.push_back(std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
+  }
+  std::nth_element(d.begin(), d.begin() + d.size() / 2, d.end());
+  return d[d.size() / 2];
+}
+
+}  // namespace gtsam_points
