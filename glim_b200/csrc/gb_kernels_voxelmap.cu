@@ -18,11 +18,12 @@
 //                        moves on -- the fixed point is exactly the table a sequential first-free-slot
 //                        insertion in ascending voxel id builds (Shun & Blelloch's phase-concurrent
 //                        deterministic hashing), including which voxels run out of probes (<= max_scan)
-//   6. host loop         num_buckets = init doubled until >= 2 V (load factor <= 0.5), then doubled again while
+//   6. host loop         num_buckets = init doubled until >= 8 V (load factor <= 1/8), then doubled again while
 //                        dropped points > drop_rate * N
 #include "gb_internal.cuh"
 
 #include <cub/cub.cuh>
+#include <stdlib.h>
 
 namespace {
 
@@ -192,7 +193,10 @@ gb_status gb_voxelmap_build_impl(gb_ctx* ctx, const gb_cloud* cloud, float resol
 
   // hash table: double until the dropped-point rate is acceptable
   int nb = init_buckets;
-  while (nb < 2 * V) nb *= 2;  // load factor <= 0.5: short probe chains (same rule as the oracle)
+  static const int load_mult = getenv("GB_TABLE_MULT") ? atoi(getenv("GB_TABLE_MULT")) : 8;  // experiment knob; 8 = the oracle's rule
+  while ((long long)nb < (long long)load_mult * V) nb *= 2;  // load factor <= 1/8: the XOR-of-primes hash clusters, and lookups that
+                                                             // MISS (65 % of them in global mapping) walk until the first empty slot
+                                                             // (profiles/tune_tablemult_r01.txt); same rule as the oracle
   for (;;) {
     GB_CUDA(cudaMalloc((void**)&m->buckets, sizeof(int4) * (size_t)nb));
     k_table_clear<<<(nb + 255) / 256, 256, 0, st>>>(nb, m->buckets);
