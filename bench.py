@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="global_mapping_gpu", choices=["single_pair", "odometry_gpu", "sub_mapping_gpu", "global_mapping_gpu", "livox_stress"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; a scaled run is not a bench value)")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"], help="multi-GPU result exchange: rows pushed into peer memory by the sweep kernel (fused) or fp32 atomics + NCCL all-reduce (nccl)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget for the cpu_baseline sample")
     return ap.parse_args()
@@ -286,7 +287,15 @@ def main():
     # ---- shard: pairs over ranks for global mapping; every other workload is a single online stream (replicas only) ----
     sharded = args.workload == "global_mapping_gpu"
     sizes = [len(c[0]) for c in w.host_clouds]
-    sweeps, slabs, my_pf, my_bytes, all_pf = [], [], 0, 0, 0
+    fused = args.collective == "fused"
+
+    def exchange(handle: bytes):
+        t = torch.tensor(list(handle), dtype=torch.uint8, device=f"cuda:{local_rank}")
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return [bytes(o.cpu().numpy().tobytes()) for o in outs]
+
+    sweeps, slabs, peers, my_pf, my_bytes, all_pf = [], [], [], 0, 0, 0
     for fset in w.sets:
         if sharded:
             f_rank, _ = multi_gpu.shard_factors(fset.factors, sizes, world)
@@ -298,7 +307,13 @@ def main():
         num_pairs = max((f.pair for f in fset.factors), default=-1) + 1
         sw = gpu.Sweep(ctx, gf, pair_index=[f.pair for f in sub.factors])
         slab = torch.zeros((max(1, num_pairs), GB_SLAB_STRIDE), dtype=torch.float32, device=f"cuda:{local_rank}")
-        sw.attach_slab(slab.data_ptr(), max(1, num_pairs))
+        if fused:
+            ps = gpu.PeerSlab(ctx, max(1, num_pairs), world if sharded else 1, rank if sharded else 0, exchange)
+            sw.attach_peer_slab(ps)
+            peers.append(ps)
+        else:
+            sw.attach_slab(slab.data_ptr(), max(1, num_pairs))
+            peers.append(None)
         sw.set_poses(sub.deltas)
         sw._sub = sub
         sweeps.append(sw)
@@ -313,11 +328,15 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if small_inputs else None
 
     def step_device():
-        for sw, slab in zip(sweeps, slabs):
-            slab.zero_()
-            sw.launch()
-            if world > 1 and sharded:
-                dist.all_reduce(slab, op=dist.ReduceOp.SUM)
+        for sw, slab, ps in zip(sweeps, slabs, peers):
+            if fused:
+                sw.launch()  # epilogue stores finished pair rows into every rank's slab
+                ps.signal_wait()  # completion flags: publish ours, wait for the peers'
+            else:
+                slab.zero_()
+                sw.launch()
+                if world > 1 and sharded:
+                    dist.all_reduce(slab, op=dist.ReduceOp.SUM)
 
     def timed(fn, steps, flush_l2):
         """K steps bracketed by barrier + synchronize; device time from CUDA events on the launching stream; max over ranks."""
@@ -395,14 +414,20 @@ def main():
     host_slabs = [torch.empty(s.shape, dtype=torch.float32, pin_memory=True) for s in slabs] if sharded else None
 
     def step_e2e():
-        for k, (sw, slab) in enumerate(zip(sweeps, slabs)):
-            slab.zero_()
+        for k, (sw, slab, ps) in enumerate(zip(sweeps, slabs, peers)):
             sw.set_poses(host_deltas[k])  # gb_sweep_set_poses: pinned staging + H2D
-            sw.launch()
-            if world > 1 and sharded:
-                dist.all_reduce(slab, op=dist.ReduceOp.SUM)
-            if sharded:
-                host_slabs[k].copy_(slab, non_blocking=True)
+            if fused:
+                sw.launch()
+                ps.signal_wait()
+                if sharded:
+                    ps.fetch()  # D2H of the complete slab
+            else:
+                slab.zero_()
+                sw.launch()
+                if world > 1 and sharded:
+                    dist.all_reduce(slab, op=dist.ReduceOp.SUM)
+                if sharded:
+                    host_slabs[k].copy_(slab, non_blocking=True)
             sw.fetch()  # gb_sweep_fetch: D2H of the gb_linearized6 records + stream sync
 
     for _ in range(3):
@@ -414,7 +439,7 @@ def main():
     # checksum of the (all-reduced) Hessian slab of one step: identical at every N up to fp32 reduction order
     step_device()
     torch.cuda.synchronize()
-    slab_checksum = float(sum(s.double().abs().sum().item() for s in slabs))
+    slab_checksum = float(sum(np.abs(ps.fetch().astype(np.float64)).sum() for ps in peers)) if fused else float(sum(s.double().abs().sum().item() for s in slabs))
     if sampler:
         time.sleep(0.15)
         sampler.stop()
@@ -423,7 +448,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, w, {"parallelism": (f"pairs sharded over {world} rank(s), NCCL all-reduce of the [{slabs[0].shape[0]} x {GB_SLAB_STRIDE}] fp32 Hessian slab" if sharded else f"replicas x{world} (single online stream does not shard)"),
+            "config": workload_config(args.workload, w, {"parallelism": ((f"pairs sharded over {world} rank(s); finished pair rows of the [{slabs[0].shape[0]} x {GB_SLAB_STRIDE}] fp32 Hessian slab are stored into every rank's buffer by the sweep kernel's epilogue over NVLink (CUDA IPC peer memory) + completion flags; no NCCL in the step" if fused else f"pairs sharded over {world} rank(s), NCCL all-reduce of the [{slabs[0].shape[0]} x {GB_SLAB_STRIDE}] fp32 Hessian slab") if sharded else f"replicas x{world} (single online stream does not shard)"),
                                                        "tiles_grid_first_sweep": [int(sweeps[0].num_tiles), int(sweeps[0].grid)], "build_seconds": round(build_s, 1), "scale": args.scale}),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ems / e_steps},
             "gpu_launches": int(gpu_launches),

@@ -21,10 +21,13 @@ SYMBOLS = [
     "gb_factor_set_linearize", "gb_factor_set_error",
     "gb_sweep_create", "gb_sweep_destroy", "gb_sweep_attach_slab", "gb_sweep_set_poses", "gb_sweep_launch", "gb_sweep_fetch",
     "gb_sweep_results_device", "gb_sweep_stats",
+    "gb_peer_slab_create", "gb_peer_slab_export", "gb_peer_slab_connect", "gb_peer_slab_destroy", "gb_sweep_attach_peer_slab",
+    "gb_peer_slab_signal_wait", "gb_peer_slab_device_ptr", "gb_peer_slab_fetch",
     "gb_overlap", "gb_covariances", "gb_find_neighbors", "gb_voxelgrid_sampling",
 ]
 
 GB_SLAB_STRIDE = 96
+GB_IPC_HANDLE_BYTES = 64
 GB_FACTOR_SURFACE_VALIDATION = 1
 
 
@@ -79,6 +82,14 @@ def lib():
     L.gb_sweep_fetch.argtypes = [vp, vp]
     L.gb_sweep_results_device.argtypes = [vp, vp]
     L.gb_sweep_stats.argtypes = [vp, vp, vp, vp, vp]
+    L.gb_peer_slab_create.argtypes = [vp, sz, i32, i32, vp]
+    L.gb_peer_slab_export.argtypes = [vp, vp]
+    L.gb_peer_slab_connect.argtypes = [vp, vp]
+    L.gb_peer_slab_destroy.argtypes = [vp]
+    L.gb_sweep_attach_peer_slab.argtypes = [vp, vp]
+    L.gb_peer_slab_signal_wait.argtypes = [vp]
+    L.gb_peer_slab_device_ptr.argtypes = [vp, vp]
+    L.gb_peer_slab_fetch.argtypes = [vp, vp]
     L.gb_overlap.argtypes = [vp, sz, vp, vp, vp, vp]
     L.gb_covariances.argtypes = [vp, sz, vp, vp, i32, i32, vp, vp]
     L.gb_find_neighbors.argtypes = [vp, sz, vp, i32, vp]

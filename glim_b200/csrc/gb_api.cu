@@ -303,6 +303,7 @@ static void sweep_free(gb_sweep* s) {
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
   if (s->d_descs) cudaFree(s->d_descs);
+  if (s->d_pair_ptr) cudaFree(s->d_pair_ptr);
   if (s->h_poses) cudaFreeHost(s->h_poses);
   delete s;
 }
@@ -335,6 +336,7 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   s->d_descs = nullptr; s->d_tiles = nullptr; s->d_poses = nullptr; s->d_poses_eval = nullptr; s->d_accum = nullptr; s->d_done = nullptr; s->d_out = nullptr;
   s->h_poses = nullptr; s->h_poses_eval = nullptr; s->h_out = nullptr; s->d_slab = nullptr; s->num_pairs = 0;
   s->d_tile_ctr = nullptr; s->ctr_base = 0;
+  s->peer = nullptr; s->d_pair_ptr = nullptr; s->d_pair_factors = nullptr; s->d_pair_done = nullptr;
   s->num_tiles = 0; s->point_factors = 0; s->algorithmic_bytes = 0; s->key = 0; s->epoch = ctx->epoch;
 
   // tile size: enough tiles to balance the persistent grid, large enough to amortise the per-tile reduction
@@ -370,6 +372,7 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     D.inv_res = fa->target->inv_res;
     D.n = (int)fa->source->n;
     D.pair = pair_index ? pair_index[f] : (int)f;
+    s->h_pair.push_back(D.pair);
     D.flags = fa->flags;
     D.first_tile = (int)tiles.size();
     // a factor with no points still gets one (empty) tile so that its epilogue runs and zeroes its record
@@ -542,6 +545,129 @@ extern "C" gb_status gb_vgicp_error(gb_factor* f, const double T_lin[16], const 
   GB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, sizeof(double) * GB_OUT_DOUBLES, cudaMemcpyDeviceToHost, f->ctx->stream));
   GB_CUDA(cudaStreamSynchronize(f->ctx->stream));
   *error = s->h_out[120];
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused multi-GPU result exchange (peer slabs over CUDA IPC)
+// ---------------------------------------------------------------------------------------------
+static size_t peer_alloc_bytes(size_t num_pairs, int world) {
+  return 2 * align_up(num_pairs * GB_SLAB_STRIDE * sizeof(float), 256) + align_up(sizeof(unsigned) * (size_t)world, 256);
+}
+
+extern "C" gb_status gb_peer_slab_create(gb_ctx* ctx, size_t num_pairs, int world, int rank, gb_peer_slab** out) {
+  GB_REQUIRE(ctx && out, "null argument");
+  GB_REQUIRE(world >= 1 && world <= GB_MAX_PEERS && rank >= 0 && rank < world, "world must be 1..8 and rank < world");
+  GB_REQUIRE(num_pairs > 0, "num_pairs must be positive");
+  *out = nullptr;
+  GB_CUDA(cudaSetDevice(ctx->device));
+  gb_peer_slab* ps = new (std::nothrow) gb_peer_slab();
+  if (!ps) return GB_ERR_INTERNAL;
+  ps->ctx = ctx; ps->num_pairs = num_pairs; ps->world = world; ps->rank = rank;
+  ps->buf_floats = align_up(num_pairs * GB_SLAB_STRIDE * sizeof(float), 256) / sizeof(float);
+  ps->local = nullptr; ps->step = 0; ps->parity = 0; ps->completed_parity = 0; ps->d_timeout = nullptr; ps->connected = (world == 1);
+  for (int p = 0; p < GB_MAX_PEERS; p++) { ps->peer[p] = nullptr; ps->opened[p] = false; }
+  const size_t bytes = peer_alloc_bytes(num_pairs, world);
+  cudaError_t e = cudaMalloc((void**)&ps->local, bytes + 256);
+  if (e != cudaSuccess) { delete ps; gb_set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
+  e = cudaMemsetAsync(ps->local, 0, bytes + 256, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { cudaFree(ps->local); delete ps; gb_set_error("peer slab init: %s", cudaGetErrorString(e)); return GB_ERR_CUDA; }
+  ps->d_timeout = (int*)(ps->local + bytes);
+  ps->peer[rank] = ps->local;
+  *out = ps;
+  return GB_OK;
+}
+
+extern "C" gb_status gb_peer_slab_export(gb_peer_slab* ps, void* handle) {
+  GB_REQUIRE(ps && handle, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == GB_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  GB_CUDA(cudaIpcGetMemHandle(&h, ps->local));
+  memcpy(handle, &h, sizeof(h));
+  return GB_OK;
+}
+
+extern "C" gb_status gb_peer_slab_connect(gb_peer_slab* ps, const void* handles) {
+  GB_REQUIRE(ps && handles, "null argument");
+  GB_CUDA(cudaSetDevice(ps->ctx->device));
+  for (int p = 0; p < ps->world; p++) {
+    if (p == ps->rank || ps->opened[p]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)p * GB_IPC_HANDLE_BYTES, sizeof(h));
+    void* ptr = nullptr;
+    GB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ps->peer[p] = (char*)ptr;
+    ps->opened[p] = true;
+  }
+  ps->connected = true;
+  return GB_OK;
+}
+
+extern "C" gb_status gb_peer_slab_destroy(gb_peer_slab* ps) {
+  if (!ps) return GB_OK;
+  cudaSetDevice(ps->ctx->device);
+  cudaStreamSynchronize(ps->ctx->stream);
+  for (int p = 0; p < ps->world; p++)
+    if (ps->opened[p]) cudaIpcCloseMemHandle(ps->peer[p]);
+  if (ps->local) cudaFree(ps->local);
+  delete ps;
+  return GB_OK;
+}
+
+extern "C" gb_status gb_sweep_attach_peer_slab(gb_sweep* s, gb_peer_slab* ps) {
+  GB_REQUIRE(s, "null sweep");
+  if (!ps) { s->peer = nullptr; return GB_OK; }
+  GB_REQUIRE(ps->ctx == s->ctx, "peer slab belongs to another context");
+  // CSR: global pair id -> this sweep's factor indices
+  const size_t P = ps->num_pairs;
+  std::vector<int> ptr(P + 1, 0), fac(s->F);
+  for (size_t f = 0; f < s->F; f++) {
+    GB_REQUIRE(s->h_pair[f] >= 0 && (size_t)s->h_pair[f] < P, "pair index out of range for this peer slab");
+    ptr[s->h_pair[f] + 1]++;
+  }
+  for (size_t k = 0; k < P; k++) ptr[k + 1] += ptr[k];
+  std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+  for (size_t f = 0; f < s->F; f++) fac[fill[s->h_pair[f]]++] = (int)f;
+  GB_CUDA(cudaSetDevice(s->ctx->device));
+  GB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  if (s->d_pair_ptr) { GB_CUDA(cudaFree(s->d_pair_ptr)); s->d_pair_ptr = nullptr; }
+  const size_t b_ptr = align_up(sizeof(int) * (P + 1), 256), b_fac = align_up(sizeof(int) * std::max<size_t>(1, s->F), 256), b_done = align_up(sizeof(unsigned) * P, 256);
+  char* d = nullptr;
+  GB_CUDA(cudaMalloc((void**)&d, b_ptr + b_fac + b_done));
+  s->d_pair_ptr = (int*)d; s->d_pair_factors = (int*)(d + b_ptr); s->d_pair_done = (unsigned*)(d + b_ptr + b_fac);
+  GB_CUDA(cudaMemcpy(s->d_pair_ptr, ptr.data(), sizeof(int) * (P + 1), cudaMemcpyHostToDevice));
+  if (s->F) GB_CUDA(cudaMemcpy(s->d_pair_factors, fac.data(), sizeof(int) * s->F, cudaMemcpyHostToDevice));
+  GB_CUDA(cudaMemset(s->d_pair_done, 0, b_done));
+  s->peer = ps;
+  return GB_OK;
+}
+
+extern "C" gb_status gb_peer_slab_signal_wait(gb_peer_slab* ps) {
+  GB_REQUIRE(ps, "null peer slab");
+  GB_REQUIRE(ps->connected, "gb_peer_slab_connect has not been called");
+  GB_CUDA(cudaSetDevice(ps->ctx->device));
+  ps->step++;
+  GB_CHECK(gb_launch_peer_signal_wait(ps));
+  ps->completed_parity = ps->parity;
+  ps->parity ^= 1;
+  return GB_OK;
+}
+
+extern "C" gb_status gb_peer_slab_device_ptr(gb_peer_slab* ps, void** device_ptr) {
+  GB_REQUIRE(ps && device_ptr, "null argument");
+  *device_ptr = ps->local + (size_t)ps->completed_parity * ps->buf_floats * sizeof(float);
+  return GB_OK;
+}
+
+extern "C" gb_status gb_peer_slab_fetch(gb_peer_slab* ps, float* host) {
+  GB_REQUIRE(ps && host, "null argument");
+  const size_t bytes = ps->num_pairs * GB_SLAB_STRIDE * sizeof(float);
+  int timeout = 0;
+  GB_CUDA(cudaMemcpyAsync(host, ps->local + (size_t)ps->completed_parity * ps->buf_floats * sizeof(float), bytes, cudaMemcpyDeviceToHost, ps->ctx->stream));
+  GB_CUDA(cudaMemcpyAsync(&timeout, ps->d_timeout, sizeof(int), cudaMemcpyDeviceToHost, ps->ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(ps->ctx->stream));
+  if (timeout) { gb_set_error("peer slab: a peer did not publish its completion flag within the timeout"); return GB_ERR_INTERNAL; }
   return GB_OK;
 }
 

@@ -94,6 +94,31 @@ struct gb_factor {
   uint64_t id;
 };
 
+#define GB_MAX_PEERS 8
+// by-value kernel parameter of the fused result exchange
+struct PeerPush {
+  int world;                      // 0 = disabled
+  float* base[GB_MAX_PEERS];      // every rank's slab buffer of the current step parity, as mapped on THIS device
+  const int* pair_ptr;            // CSR over global pair ids -> local factor indices (empty for pairs owned elsewhere)
+  const int* pair_factors;
+  unsigned* pair_done;            // per-pair tickets, self-cleaning
+};
+
+struct gb_peer_slab {
+  gb_ctx* ctx;
+  size_t num_pairs;
+  int world, rank;
+  size_t buf_floats;              // floats per buffer
+  char* local;                    // cudaMalloc: [buffer 0][buffer 1][flags: world x u32, padded]
+  char* peer[GB_MAX_PEERS];       // every rank's allocation as mapped here (peer[rank] == local)
+  bool opened[GB_MAX_PEERS];
+  unsigned step;                  // last launched step
+  int parity;                     // buffer written by the NEXT launch
+  int completed_parity;           // buffer completed by the last signal_wait
+  int* d_timeout;
+  bool connected;
+};
+
 #define GB_ACC_STRIDE 32      // doubles per factor in the accumulation buffer (29 used)
 #define GB_OUT_DOUBLES 122    // gb_linearized6
 
@@ -115,6 +140,11 @@ struct gb_sweep {
   double* h_out;          // pinned
   float* d_slab;
   size_t num_pairs;
+  gb_peer_slab* peer;             // fused exchange target (or nullptr)
+  int* d_pair_ptr;                // CSR pair -> factors (device), built when a peer slab is attached
+  int* d_pair_factors;
+  unsigned* d_pair_done;
+  std::vector<int> h_pair;        // pair id per factor
   int num_tiles, tile_size, grid;   // work items, points per item, CTAs
   int min_blocks;                   // kernel register-budget variant (CTAs per SM)
   uint64_t point_factors, algorithmic_bytes;
@@ -143,6 +173,7 @@ gb_status gb_ctx_pinned(gb_ctx* ctx, size_t bytes, void** out);   // pinned host
 // kernel launchers (gb_kernels_*.cu)
 enum { GB_MODE_LINEARIZE = 0, GB_MODE_ERROR = 1 };
 gb_status gb_launch_sweep(gb_sweep* s, int mode);
+gb_status gb_launch_peer_signal_wait(gb_peer_slab* ps);
 gb_status gb_launch_overlap(gb_ctx* ctx, int num_targets, const FactorDesc* d_descs, const double* d_poses, int n, int* d_count);
 gb_status gb_cloud_reorder_impl(gb_ctx* ctx, gb_cloud* c, const void* staged /* device copy of the planes in original order */, size_t b0, size_t b1, size_t b2, size_t b3);
 size_t gb_cloud_reorder_scratch_bytes(size_t n, size_t staged_bytes);

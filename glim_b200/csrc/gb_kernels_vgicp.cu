@@ -21,6 +21,8 @@
 // the accumulator for the next sweep.
 #include "gb_internal.cuh"
 
+#include <string.h>
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -96,6 +98,53 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane)
 }
 
 // fp64 epilogue of one factor, executed by warp 0 of the CTA that retired the factor's last tile.
+// slab row element e (see GB_SLAB_STRIDE in include/glim_b200.h) -> index in the 122-double record
+__device__ __forceinline__ int slab_to_record(int e) {
+  if (e < 21 || (e >= 57 && e < 78)) {  // upper triangles of H_tt / H_ss, row-major (i <= j)
+    int u = e < 21 ? e : e - 57, i = 0;
+    while (u >= 6 - i) { u -= 6 - i; i++; }
+    const int j = i + u;
+    return (e < 21 ? 0 : 36) + j * 6 + i;
+  }
+  if (e < 57) return 72 + (e - 21);   // H_ts, column-major as in the record
+  if (e < 84) return 108 + (e - 78);  // b_t
+  if (e < 90) return 114 + (e - 84);  // b_s
+  return 120 + (e - 90);              // error, num_inliers
+}
+
+// Fused result exchange: executed by the warp that completed factor f.  If f was the LAST factor of its pair, sum the
+// pair's records (fp64, fixed order -> deterministic), and store the fp32 row into every rank's slab (128-bit stores;
+// peers are reached through their IPC-mapped addresses over NVLink).
+__device__ void pair_push(int f, const FactorDesc& D, const double* __restrict__ out, const PeerPush& peer, float* row /* 96 floats of shared memory */) {
+  const int lane = threadIdx.x & 31;
+  __threadfence();  // this factor's record is visible before the ticket
+  __syncwarp();
+  int last = 0;
+  const int pb = peer.pair_ptr[D.pair], pe = peer.pair_ptr[D.pair + 1];
+  if (lane == 0) {
+    const unsigned t = atomicAdd(&peer.pair_done[D.pair], 1u);
+    last = (t == (unsigned)(pe - pb) - 1u);
+    if (last) peer.pair_done[D.pair] = 0u;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence();
+  for (int e = lane; e < GB_SLAB_STRIDE; e += 32) {
+    double s = 0.0;
+    if (e < 92) {
+      const int r = slab_to_record(e);
+      for (int k = pb; k < pe; k++) s += __ldcg(&out[(size_t)peer.pair_factors[k] * GB_OUT_DOUBLES + r]);
+    }
+    row[e] = (float)s;
+  }
+  __syncwarp();
+  if (lane < GB_SLAB_STRIDE / 4) {
+    const float4 v = reinterpret_cast<const float4*>(row)[lane];
+    for (int p = 0; p < peer.world; p++) reinterpret_cast<float4*>(peer.base[p] + (size_t)D.pair * GB_SLAB_STRIDE)[lane] = v;
+  }
+  (void)f;
+}
+
 __device__ void factor_epilogue(int f, const FactorDesc& D, const double* __restrict__ poses, double* __restrict__ accum, double* __restrict__ out, float* __restrict__ slab, double* sm /* >= 36+36+36+32 doubles */) {
   const int lane = threadIdx.x & 31;
   double* A = sm;            // 32 accumulators
@@ -195,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
   const FactorDesc* __restrict__ descs, const double* __restrict__ poses, const double* __restrict__ poses_eval,
   const int2* __restrict__ items, int num_items, int chunk,
   unsigned long long* __restrict__ item_ctr, unsigned long long ctr_base,
-  double* __restrict__ accum, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab) {
+  double* __restrict__ accum, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab, const PeerPush peer) {
   __shared__ __align__(16) uint2 s_q[kWarps][kSubMax];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -340,6 +389,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
       __threadfence();
       factor_epilogue(f, D, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, out, slab, reinterpret_cast<double*>(q));
       __syncwarp();
+      if (MODE == GB_MODE_LINEARIZE && peer.world > 0) pair_push(f, D, out, peer, reinterpret_cast<float*>(q) + 512);
+      __syncwarp();
     }
     item = __shfl_sync(0xffffffffu, next_item, 0);
   }
@@ -376,7 +427,34 @@ __global__ void __launch_bounds__(256) k_overlap(int num_targets, const FactorDe
 
 template <int MODE, int MINB>
 static void launch_variant(gb_sweep* s, const double* poses_eval, float* slab) {
-  k_vgicp_sweep<MODE, MINB><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->d_done, s->d_out, slab);
+  PeerPush pp;
+  memset(&pp, 0, sizeof(pp));
+  if (MODE == GB_MODE_LINEARIZE && s->peer) {
+    gb_peer_slab* ps = s->peer;
+    pp.world = ps->world;
+    for (int p = 0; p < ps->world; p++) pp.base[p] = reinterpret_cast<float*>(ps->peer[p]) + (size_t)ps->parity * ps->buf_floats;
+    pp.pair_ptr = s->d_pair_ptr; pp.pair_factors = s->d_pair_factors; pp.pair_done = s->d_pair_done;
+  }
+  k_vgicp_sweep<MODE, MINB><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->d_done, s->d_out, slab, pp);
+}
+
+// completion flags of the fused exchange: one thread per rank publishes this rank's step to that peer, then waits for the
+// peer's flag.  The preceding sweep kernel has completed (stream order), so all its peer stores have been performed.
+struct PeerFlags { unsigned* flags[GB_MAX_PEERS]; };
+__global__ void k_peer_signal_wait(PeerFlags pf, int world, int rank, unsigned step, int* timeout) {
+  const int t = threadIdx.x;
+  if (t >= world) return;
+  __threadfence_system();
+  volatile unsigned* remote = pf.flags[t] + rank;
+  *remote = step;
+  __threadfence_system();
+  volatile unsigned* mine = pf.flags[rank] + t;
+  const long long t0 = clock64();
+  while ((int)(*mine - step) < 0) {
+    __nanosleep(200);
+    if (clock64() - t0 > 20000000000ll) { *timeout = 1; break; }  // ~10 s: a peer died; do not hang the GPU
+  }
+  __threadfence_system();
 }
 
 gb_status gb_launch_sweep(gb_sweep* s, int mode) {
@@ -397,6 +475,16 @@ gb_status gb_launch_sweep(gb_sweep* s, int mode) {
   // every warp draws tickets until it gets one past the end: the counter advances by num_items + warps per launch
   s->ctr_base += (unsigned long long)s->num_tiles + (unsigned long long)s->grid * kWarps;
   ctx->launches++;
+  return GB_OK;
+}
+
+gb_status gb_launch_peer_signal_wait(gb_peer_slab* ps) {
+  PeerFlags pf;
+  memset(&pf, 0, sizeof(pf));
+  for (int p = 0; p < ps->world; p++) pf.flags[p] = reinterpret_cast<unsigned*>(ps->peer[p] + 2 * ps->buf_floats * sizeof(float));
+  k_peer_signal_wait<<<1, 32, 0, ps->ctx->stream>>>(pf, ps->world, ps->rank, ps->step, ps->d_timeout);
+  GB_CUDA(cudaGetLastError());
+  ps->ctx->launches++;
   return GB_OK;
 }
 

@@ -294,6 +294,10 @@ class Sweep:
         check(lib().gb_sweep_stats(h, C.byref(pf), C.byref(ab), C.byref(nt), C.byref(gs)))
         self.point_factors, self.algorithmic_bytes, self.num_tiles, self.grid = pf.value, ab.value, nt.value, gs.value
 
+    def attach_peer_slab(self, peer_slab: "PeerSlab | None"):
+        self._peer = peer_slab  # keep alive
+        check(lib().gb_sweep_attach_peer_slab(self.h, peer_slab.h if peer_slab is not None else None))
+
     def attach_slab(self, device_ptr: int, num_pairs: int):
         check(lib().gb_sweep_attach_slab(self.h, C.c_void_p(device_ptr), num_pairs))
 
@@ -317,6 +321,44 @@ class Sweep:
     def __del__(self):
         if getattr(self, "h", None) and self.ctx.h:
             lib().gb_sweep_destroy(self.h)
+            self.h = None
+
+
+class PeerSlab:
+    """gb_peer_slab: ping-pong fp32 [num_pairs][96] result buffers shared with the other ranks of the box through CUDA
+    IPC; the sweep's epilogue stores finished pair rows straight into every rank's buffer (multi-GPU exchange fused into
+    the kernel).  `exchange(handle_bytes) -> list[bytes]` must all-gather the 64-byte handles in rank order
+    (torch.distributed in the bench); with world == 1 nothing is exchanged."""
+
+    def __init__(self, ctx: Context, num_pairs: int, world: int = 1, rank: int = 0, exchange=None):
+        self.ctx, self.num_pairs, self.world, self.rank = ctx, num_pairs, world, rank
+        h = C.c_void_p()
+        check(lib().gb_peer_slab_create(ctx.h, num_pairs, world, rank, C.byref(h)))
+        self.h = h
+        if world > 1:
+            buf = (C.c_ubyte * capi.GB_IPC_HANDLE_BYTES)()
+            check(lib().gb_peer_slab_export(self.h, C.cast(buf, C.c_void_p)))
+            handles = exchange(bytes(buf))
+            assert len(handles) == world and all(len(x) == capi.GB_IPC_HANDLE_BYTES for x in handles)
+            blob = (C.c_ubyte * (capi.GB_IPC_HANDLE_BYTES * world)).from_buffer_copy(b"".join(handles))
+            check(lib().gb_peer_slab_connect(self.h, C.cast(blob, C.c_void_p)))
+
+    def signal_wait(self):
+        check(lib().gb_peer_slab_signal_wait(self.h))
+
+    def fetch(self) -> np.ndarray:
+        out = np.empty((self.num_pairs, capi.GB_SLAB_STRIDE), np.float32)
+        check(lib().gb_peer_slab_fetch(self.h, ptr(out)))
+        return out
+
+    def device_ptr(self) -> int:
+        p = C.c_void_p()
+        check(lib().gb_peer_slab_device_ptr(self.h, C.byref(p)))
+        return p.value or 0
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            lib().gb_peer_slab_destroy(self.h)
             self.h = None
 
 

@@ -140,6 +140,27 @@ GB_API gb_status gb_sweep_results_device(gb_sweep* sweep, void** device_ptr);   
 /* bookkeeping for the roofline: sum of N_source, and algorithmic bytes B_sweep of SURVEY 8(d) */
 GB_API gb_status gb_sweep_stats(const gb_sweep* sweep, uint64_t* point_factors, uint64_t* algorithmic_bytes, uint32_t* num_tiles, uint32_t* grid_size);
 
+/* ---- Multi-GPU result exchange fused into the sweep (no reference counterpart: GLIM is single-GPU).
+ *      A gb_peer_slab is a pair of fp32 buffers [num_pairs][GB_SLAB_STRIDE] (ping-pong by step parity) plus completion
+ *      flags, allocated with cudaMalloc and shared with the other ranks of the box through CUDA IPC.  When one is attached
+ *      to a sweep, the epilogue of the LAST factor of every pair sums the pair's factor records in fp64 and stores the
+ *      finished row with 128-bit stores straight into EVERY rank's buffer over NVLink (each pair is owned by exactly one
+ *      rank, so the "all-reduce" is an all-gather done by the producers); gb_peer_slab_signal_wait() then publishes this
+ *      rank's completion flag to all peers and waits for theirs.  No NCCL call, no memset, no float atomics (rows are
+ *      deterministic).  With world == 1 it is simply the deterministic way to get the pair slab. ---- */
+#define GB_IPC_HANDLE_BYTES 64
+typedef struct gb_peer_slab gb_peer_slab;
+GB_API gb_status gb_peer_slab_create(gb_ctx* ctx, size_t num_pairs, int world, int rank, gb_peer_slab** out);
+GB_API gb_status gb_peer_slab_export(gb_peer_slab* slab, void* handle /* GB_IPC_HANDLE_BYTES */);
+GB_API gb_status gb_peer_slab_connect(gb_peer_slab* slab, const void* handles /* world x GB_IPC_HANDLE_BYTES, rank order */);
+GB_API gb_status gb_peer_slab_destroy(gb_peer_slab* slab);
+GB_API gb_status gb_sweep_attach_peer_slab(gb_sweep* sweep, gb_peer_slab* slab);
+/* after gb_sweep_launch: publish completion of this step to every peer, wait (on the stream) until every peer has published */
+GB_API gb_status gb_peer_slab_signal_wait(gb_peer_slab* slab);
+/* the buffer completed by the last gb_peer_slab_signal_wait: device pointer / copy to host (D2H + stream sync) */
+GB_API gb_status gb_peer_slab_device_ptr(gb_peer_slab* slab, void** device_ptr);
+GB_API gb_status gb_peer_slab_fetch(gb_peer_slab* slab, float* host /* num_pairs x GB_SLAB_STRIDE */);
+
 /* ---- overlap_gpu(voxelmap, source, delta, stream) / overlap_gpu(voxelmaps, source, deltas, stream) /
  *      overlap_auto (odometry_estimation_gpu.cpp:231,248,265,279; sub_mapping.cpp:252; global_mapping.cpp:322,448):
  *      fraction of source points that fall in an occupied voxel of any target ---- */

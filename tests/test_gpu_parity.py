@@ -207,6 +207,36 @@ def test_pair_slab_accumulates_levels(ctx, dev):
     assert s[1][91] == rec[0]["num_inliers"] + rec[1]["num_inliers"]
 
 
+def test_peer_slab_world1_is_deterministic_sum_of_levels(ctx, dev):
+    """Fused exchange with world == 1: the epilogue of a pair's last factor sums the pair's records in fp64 and stores the
+    fp32 row (no float atomics): rows equal the sum of the levels, untouched pairs stay zero, repeated steps are bit-identical
+    (ping-pong buffers), and the values agree with the atomic-slab path."""
+    from glim_b200 import multi_gpu
+
+    maps0 = [gpu.GaussianVoxelMapGPU(r, ctx=ctx).insert(dev["cloud"][0]) for r in (0.25, 0.5)]
+    maps1 = [gpu.GaussianVoxelMapGPU(r, ctx=ctx).insert(dev["cloud"][1]) for r in (0.25, 0.5)]
+    T = dev["T_gt"]
+    facs = [gpu.IntegratedVGICPFactorGPU(0, 1, m, dev["cloud"][1], ctx=ctx) for m in maps0] + [gpu.IntegratedVGICPFactorGPU(1, 0, m, dev["cloud"][0], ctx=ctx) for m in maps1]
+    sw = gpu.Sweep(ctx, facs, pair_index=[3, 3, 0, 0])
+    ps = gpu.PeerSlab(ctx, 5)
+    sw.attach_peer_slab(ps)
+    sw.set_poses(np.stack([T, T, synth.inv_pose(T), synth.inv_pose(T)]))
+    rows = []
+    for _ in range(3):
+        sw.launch()
+        ps.signal_wait()
+        rows.append(ps.fetch())
+    rec = sw.fetch()
+    assert rows[0].tobytes() == rows[1].tobytes() == rows[2].tobytes()
+    assert not rows[0][[1, 2, 4]].any()
+    for pair, (a, b) in ((3, (0, 1)), (0, (2, 3))):
+        got = multi_gpu.unpack_slab_row(rows[0][pair])
+        for k in ("H_tt", "H_ss", "H_ts", "b_t", "b_s"):
+            want = gpu.unpack_linearized(rec[a])[k] + gpu.unpack_linearized(rec[b])[k]
+            assert np.allclose(got[k], want, rtol=2e-7, atol=2e-7 * np.abs(want).max())
+        assert got["num_inliers"] == rec[a]["num_inliers"] + rec[b]["num_inliers"]
+
+
 # ---------------------------------------------------------------------------------------------- preprocess kernels
 def test_covariances_match_oracle(ctx, pair):
     from glim_b200 import preprocess
