@@ -83,7 +83,7 @@ def workload_config(name, w, extra):
         "point_factors_per_step": int(w.point_factors),
         "l2": "inputs larger than L2 (no flush)" if sum(len(c[0]) for c in w.host_clouds) * 36 > 126e6 else "L2 flushed between steps (256 MB write)",
     }
-    cfg.update(w.notes)
+    cfg.update({k: v for k, v in w.notes.items() if not k.startswith("_")})
     cfg.update(extra)
     return cfg
 
@@ -298,7 +298,7 @@ def main():
     sweeps, slabs, peers, my_pf, my_bytes, all_pf = [], [], [], 0, 0, 0
     for fset in w.sets:
         if sharded:
-            f_rank, _ = multi_gpu.shard_factors(fset.factors, sizes, world)
+            f_rank, _ = multi_gpu.shard_factors(fset.factors, sizes, world, pair_cost=w.notes.get("_pair_overlap"))
             mine = [k for k in range(len(fset.factors)) if f_rank[k] == rank]
         else:
             mine = list(range(len(fset.factors)))
@@ -420,7 +420,7 @@ def main():
                 sw.launch()
                 ps.signal_wait()
                 if sharded:
-                    ps.fetch()  # D2H of the complete slab
+                    ps.fetch_async()  # D2H of the complete slab into pinned memory; the sync below covers it
             else:
                 slab.zero_()
                 sw.launch()

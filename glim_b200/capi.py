@@ -22,7 +22,7 @@ SYMBOLS = [
     "gb_sweep_create", "gb_sweep_destroy", "gb_sweep_attach_slab", "gb_sweep_set_poses", "gb_sweep_launch", "gb_sweep_fetch",
     "gb_sweep_results_device", "gb_sweep_stats",
     "gb_peer_slab_create", "gb_peer_slab_export", "gb_peer_slab_connect", "gb_peer_slab_destroy", "gb_sweep_attach_peer_slab",
-    "gb_peer_slab_signal_wait", "gb_peer_slab_device_ptr", "gb_peer_slab_fetch",
+    "gb_peer_slab_signal_wait", "gb_peer_slab_device_ptr", "gb_peer_slab_fetch", "gb_peer_slab_fetch_async",
     "gb_overlap", "gb_covariances", "gb_find_neighbors", "gb_voxelgrid_sampling",
 ]
 
@@ -90,6 +90,7 @@ def lib():
     L.gb_peer_slab_signal_wait.argtypes = [vp]
     L.gb_peer_slab_device_ptr.argtypes = [vp, vp]
     L.gb_peer_slab_fetch.argtypes = [vp, vp]
+    L.gb_peer_slab_fetch_async.argtypes = [vp, vp]
     L.gb_overlap.argtypes = [vp, sz, vp, vp, vp, vp]
     L.gb_covariances.argtypes = [vp, sz, vp, vp, i32, i32, vp, vp]
     L.gb_find_neighbors.argtypes = [vp, sz, vp, i32, vp]

@@ -575,6 +575,9 @@ extern "C" gb_status gb_peer_slab_create(gb_ctx* ctx, size_t num_pairs, int worl
   if (e != cudaSuccess) { cudaFree(ps->local); delete ps; gb_set_error("peer slab init: %s", cudaGetErrorString(e)); return GB_ERR_CUDA; }
   ps->d_timeout = (int*)(ps->local + bytes);
   ps->peer[rank] = ps->local;
+  ps->h_pinned = nullptr;
+  e = cudaMallocHost((void**)&ps->h_pinned, num_pairs * GB_SLAB_STRIDE * sizeof(float) + 64);
+  if (e != cudaSuccess) { cudaFree(ps->local); delete ps; gb_set_error("cudaMallocHost: %s", cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
   *out = ps;
   return GB_OK;
 }
@@ -611,6 +614,7 @@ extern "C" gb_status gb_peer_slab_destroy(gb_peer_slab* ps) {
   for (int p = 0; p < ps->world; p++)
     if (ps->opened[p]) cudaIpcCloseMemHandle(ps->peer[p]);
   if (ps->local) cudaFree(ps->local);
+  if (ps->h_pinned) cudaFreeHost(ps->h_pinned);
   delete ps;
   return GB_OK;
 }
@@ -660,14 +664,24 @@ extern "C" gb_status gb_peer_slab_device_ptr(gb_peer_slab* ps, void** device_ptr
   return GB_OK;
 }
 
+extern "C" gb_status gb_peer_slab_fetch_async(gb_peer_slab* ps, const float** host_ptr) {
+  GB_REQUIRE(ps, "null peer slab");
+  const size_t bytes = ps->num_pairs * GB_SLAB_STRIDE * sizeof(float);
+  GB_CUDA(cudaMemcpyAsync(ps->h_pinned, ps->local + (size_t)ps->completed_parity * ps->buf_floats * sizeof(float), bytes, cudaMemcpyDeviceToHost, ps->ctx->stream));
+  GB_CUDA(cudaMemcpyAsync((char*)ps->h_pinned + bytes, ps->d_timeout, sizeof(int), cudaMemcpyDeviceToHost, ps->ctx->stream));
+  if (host_ptr) *host_ptr = ps->h_pinned;
+  return GB_OK;
+}
+
 extern "C" gb_status gb_peer_slab_fetch(gb_peer_slab* ps, float* host) {
   GB_REQUIRE(ps && host, "null argument");
   const size_t bytes = ps->num_pairs * GB_SLAB_STRIDE * sizeof(float);
-  int timeout = 0;
-  GB_CUDA(cudaMemcpyAsync(host, ps->local + (size_t)ps->completed_parity * ps->buf_floats * sizeof(float), bytes, cudaMemcpyDeviceToHost, ps->ctx->stream));
-  GB_CUDA(cudaMemcpyAsync(&timeout, ps->d_timeout, sizeof(int), cudaMemcpyDeviceToHost, ps->ctx->stream));
+  GB_CHECK(gb_peer_slab_fetch_async(ps, nullptr));
   GB_CUDA(cudaStreamSynchronize(ps->ctx->stream));
+  int timeout = 0;
+  memcpy(&timeout, (char*)ps->h_pinned + bytes, sizeof(int));
   if (timeout) { gb_set_error("peer slab: a peer did not publish its completion flag within the timeout"); return GB_ERR_INTERNAL; }
+  memcpy(host, ps->h_pinned, bytes);
   return GB_OK;
 }
 

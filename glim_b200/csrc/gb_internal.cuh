@@ -116,6 +116,7 @@ struct gb_peer_slab {
   int parity;                     // buffer written by the NEXT launch
   int completed_parity;           // buffer completed by the last signal_wait
   int* d_timeout;
+  float* h_pinned;                // num_pairs x GB_SLAB_STRIDE, for the fetches
   bool connected;
 };
 

@@ -351,6 +351,12 @@ class PeerSlab:
         check(lib().gb_peer_slab_fetch(self.h, ptr(out)))
         return out
 
+    def fetch_async(self) -> np.ndarray:
+        """Enqueue the D2H into the slab's pinned buffer; the returned view is valid after the next stream sync."""
+        p = C.POINTER(C.c_float)()
+        check(lib().gb_peer_slab_fetch_async(self.h, C.byref(p)))
+        return np.ctypeslib.as_array(p, shape=(self.num_pairs, capi.GB_SLAB_STRIDE))
+
     def device_ptr(self) -> int:
         p = C.c_void_p()
         check(lib().gb_peer_slab_device_ptr(self.h, C.byref(p)))

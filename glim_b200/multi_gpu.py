@@ -27,13 +27,16 @@ def lpt_partition(weights, n_parts: int):
     return part
 
 
-def shard_factors(factors, source_sizes, world: int):
-    """factors: objects with .pair and .source; -> (rank per factor, rank per pair).  Pairs are kept whole."""
+def shard_factors(factors, source_sizes, world: int, pair_cost=None):
+    """factors: objects with .pair and .source; -> (rank per factor, rank per pair).  Pairs are kept whole.
+    pair_cost (optional): pair -> expected inlier fraction (the overlap the gate measured): a hit costs ~4x a miss in the
+    sweep kernel, so the weight of a factor is n_source * (1 + 3 * overlap)."""
     pairs = sorted({f.pair for f in factors})
     index = {p: k for k, p in enumerate(pairs)}
     w = np.zeros(len(pairs))
     for f in factors:
-        w[index[f.pair]] += source_sizes[f.source]
+        c = 1.0 + 3.0 * float(pair_cost[f.pair]) if pair_cost is not None and f.pair in pair_cost else 1.0
+        w[index[f.pair]] += source_sizes[f.source] * c
     pair_rank = lpt_partition(w, world)
     return np.array([pair_rank[index[f.pair]] for f in factors], dtype=np.int64), {p: int(pair_rank[index[p]]) for p in pairs}
 

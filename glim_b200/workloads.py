@@ -319,6 +319,7 @@ def global_mapping(ctx, n_submaps=256, laps=4, sensor="os1_64", n_rays=None, par
     w.upload()
     w.build_maps()
     factors, pair = [], 0
+    pair_overlap = {}
     d2max = p.max_implicit_loop_distance**2
     for cur in range(1, n_submaps):
         for i in range(cur):
@@ -329,8 +330,10 @@ def global_mapping(ctx, n_submaps=256, laps=4, sensor="os1_64", n_rays=None, par
                 continue
             for l in range(p.submap_voxelmap_levels):  # :462-467
                 factors.append(Factor(i, l, cur, pair))
+            pair_overlap[pair] = ov
             pair += 1
     w.notes["num_pairs"] = pair
+    w.notes["_pair_overlap"] = pair_overlap  # used to balance the multi-GPU partition
     w.sets.append(FactorSet(factors, w.noisy_deltas(factors, synth.rng_for(402), 0.02, 0.2)))
     return w
 

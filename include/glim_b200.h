@@ -160,6 +160,9 @@ GB_API gb_status gb_peer_slab_signal_wait(gb_peer_slab* slab);
 /* the buffer completed by the last gb_peer_slab_signal_wait: device pointer / copy to host (D2H + stream sync) */
 GB_API gb_status gb_peer_slab_device_ptr(gb_peer_slab* slab, void** device_ptr);
 GB_API gb_status gb_peer_slab_fetch(gb_peer_slab* slab, float* host /* num_pairs x GB_SLAB_STRIDE */);
+/* same copy into the slab's own pinned host buffer, WITHOUT synchronizing: valid after the next synchronization of the
+ * context's stream (e.g. gb_sweep_fetch); *host_ptr receives the pinned buffer */
+GB_API gb_status gb_peer_slab_fetch_async(gb_peer_slab* slab, const float** host_ptr);
 
 /* ---- overlap_gpu(voxelmap, source, delta, stream) / overlap_gpu(voxelmaps, source, deltas, stream) /
  *      overlap_auto (odometry_estimation_gpu.cpp:231,248,265,279; sub_mapping.cpp:252; global_mapping.cpp:322,448):
