@@ -212,9 +212,10 @@ __device__ void factor_epilogue(int f, const FactorDesc& D, const double* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// The sweep kernel.  Persistent grid of independent WARPS: every warp draws work items from a
-// global queue (one atomic per item; the counter is monotonic across launches so it never needs a
-// reset).  An item = up to `chunk` consecutive source points of one factor, processed in rounds of
+// The sweep kernel.  Persistent grid of independent WARPS: every warp starts on the item with its own
+// index and then draws further work items from a global queue (one atomic per item; the counter is
+// monotonic across launches so it never needs a reset; sweeps with no more items than warps use no
+// queue at all).  An item = up to `chunk` consecutive source points of one factor, processed in rounds of
 // kSubMax points with two warp-local phases:
 //   A (lookup, all lanes busy): 16-byte read of (x, y, z, c00), transform, voxel coordinate, hash
 //     probe (4 points per lane in flight); hits are COMPACTED into the warp's shared-memory queue as (point, voxel) pairs with
@@ -250,13 +251,15 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
   const unsigned lt_mask = (1u << lane) - 1u;
   uint2* __restrict__ q = s_q[warp];
 
-  int item = 0;
-  if (lane == 0) item = (int)(atomicAdd(item_ctr, 1ull) - ctr_base);
-  item = __shfl_sync(0xffffffffu, item, 0);
+  // first item: static (warp id) -- thousands of warps hammering one atomic at kernel start cost ~10 us, which is most of
+  // a small odometry sweep; further items (only when there are more items than warps) come from the global queue
+  const int total_warps = gridDim.x * kWarps;
+  const bool dynamic = num_items > total_warps;
+  int item = blockIdx.x * kWarps + warp;
 
   while (item < num_items) {
-    int next_item = 0;
-    if (lane == 0) next_item = (int)(atomicAdd(item_ctr, 1ull) - ctr_base);  // latency hidden behind the item
+    int next_item = 0x7fffffff;
+    if (dynamic && lane == 0) next_item = (int)(atomicAdd(item_ctr, 1ull) - ctr_base) + total_warps;  // latency hidden behind the item
     const int2 it = __ldg(&items[item]);
     const int f = it.x;
     const FactorDesc D = descs[f];
@@ -472,8 +475,8 @@ gb_status gb_launch_sweep(gb_sweep* s, int mode) {
     else launch_variant<GB_MODE_ERROR, 2>(s, s->d_poses_eval, nullptr);
   }
   GB_CUDA(cudaGetLastError());
-  // every warp draws tickets until it gets one past the end: the counter advances by num_items + warps per launch
-  s->ctr_base += (unsigned long long)s->num_tiles + (unsigned long long)s->grid * kWarps;
+  // every processed item draws exactly one ticket from the queue (when the queue is in use at all)
+  if (s->num_tiles > s->grid * kWarps) s->ctr_base += (unsigned long long)s->num_tiles;
   ctx->launches++;
   return GB_OK;
 }

@@ -27,17 +27,34 @@ def lpt_partition(weights, n_parts: int):
     return part
 
 
-def shard_factors(factors, source_sizes, world: int, pair_cost=None):
-    """factors: objects with .pair and .source; -> (rank per factor, rank per pair).  Pairs are kept whole.
-    pair_cost (optional): pair -> expected inlier fraction (the overlap the gate measured): a hit costs ~4x a miss in the
-    sweep kernel, so the weight of a factor is n_source * (1 + 3 * overlap)."""
-    pairs = sorted({f.pair for f in factors})
+def shard_factors(factors, source_sizes, world: int, pair_cost=None, contiguous=True):
+    """factors: objects with .pair and .source, in the order the reference creates them (source-major: all factors of one
+    new submap are consecutive, global_mapping.cpp:441-470); -> (rank per factor, rank per pair).  Pairs are kept whole.
+
+    pair_cost (optional): pair -> expected inlier fraction (the overlap the gate measured).  In the sweep kernel a hit costs
+    ~2.2x a miss (fit to the measured sub-mapping / global-mapping throughputs), so a factor weighs n_source * (1 + 1.25 * overlap).
+
+    contiguous=True (default): cut the factor list into `world` consecutive chunks of equal total weight.  Every rank then
+    keeps ALL factors of the source clouds it touches, so a source cloud is read from HBM once per rank-sweep and served from
+    L2 to the ~26 factors that share it -- exactly the reuse a single GPU gets.  contiguous=False: longest-processing-time
+    first (best balance, but scatters the factors of one source over all ranks)."""
+    pairs = []
+    seen = set()
+    for f in factors:
+        if f.pair not in seen:
+            seen.add(f.pair)
+            pairs.append(f.pair)
     index = {p: k for k, p in enumerate(pairs)}
     w = np.zeros(len(pairs))
     for f in factors:
-        c = 1.0 + 3.0 * float(pair_cost[f.pair]) if pair_cost is not None and f.pair in pair_cost else 1.0
+        c = 1.0 + 1.25 * float(pair_cost[f.pair]) if pair_cost is not None and f.pair in pair_cost else 1.0
         w[index[f.pair]] += source_sizes[f.source] * c
-    pair_rank = lpt_partition(w, world)
+    if contiguous:
+        cum = np.cumsum(w) - 0.5 * w  # midpoint rule: a pair goes to the chunk its centre of mass falls in
+        total = float(w.sum()) or 1.0
+        pair_rank = np.minimum(world - 1, (cum / total * world).astype(np.int64))
+    else:
+        pair_rank = lpt_partition(w, world)
     return np.array([pair_rank[index[f.pair]] for f in factors], dtype=np.int64), {p: int(pair_rank[index[p]]) for p in pairs}
 
 
