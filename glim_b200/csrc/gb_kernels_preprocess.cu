@@ -10,6 +10,10 @@
 #include "gb_internal.cuh"
 
 #include <cub/cub.cuh>
+#include <cmath>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
 
 namespace {
 
@@ -66,6 +70,124 @@ __global__ void __launch_bounds__(128) k_knn_bruteforce(int n, const double4* __
 #pragma unroll
     for (int k = 0; k < K; k++) neighbors[(size_t)i * K + k] = k < found ? bi[k] : i;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact k-NN on a uniform grid.  Points are sorted by the packed key of their cell (x major, z minor), so the cells of one
+// (x, y) column with consecutive z are one contiguous key range: a ring of the search cube costs (2r+1)^2 binary searches.
+// One query per thread, in sorted order (spatially coherent warps).  After ring r every unseen point lies outside the cube
+// of cells [c-r, c+r]^3, i.e. at least m*h away (m = distance from the query to the nearest cube face, in cells), so the
+// search stops as soon as the k-th best distance is within that bound -- the result is EXACT, with the same
+// (distance, index) tie rule and the same un-contracted fp64 distance as the brute-force kernel and the oracle.
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned long long kKnnInvalid = ~0ull;
+
+__global__ void k_knn_keys(int n, const double4* __restrict__ pts, double inv_h, unsigned long long* __restrict__ keys, int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 p = pts[i];
+  unsigned long long key = kKnnInvalid;
+  if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+    const double fx = floor(p.x * inv_h), fy = floor(p.y * inv_h), fz = floor(p.z * inv_h);
+    if (fabs(fx) < 1048575.0 && fabs(fy) < 1048575.0 && fabs(fz) < 1048575.0) {
+      unsigned long long k;
+      if (gb_pack_key((int)fx, (int)fy, (int)fz, &k)) key = k;
+    }
+  }
+  keys[i] = key;
+  idx[i] = i;
+}
+__global__ void k_knn_gather(int n, const int* __restrict__ idx_s, const double4* __restrict__ pts, double4* __restrict__ pts_s) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) pts_s[s] = pts[idx_s[s]];
+}
+__global__ void k_count_heads(int n, const unsigned long long* __restrict__ keys_s, int* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int head = 0;
+  if (i < n) { const unsigned long long k = keys_s[i]; head = (k != kKnnInvalid && (i == 0 || keys_s[i - 1] != k)) ? 1 : 0; }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) head += __shfl_xor_sync(0xffffffffu, head, o);
+  if ((threadIdx.x & 31) == 0 && head) atomicAdd(count, head);
+}
+
+__device__ __forceinline__ int knn_lower_bound(const unsigned long long* __restrict__ keys, int n, unsigned long long key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(&keys[mid]) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) k_knn_grid(int n, const double4* __restrict__ pts_s, const unsigned long long* __restrict__ keys_s, const int* __restrict__ idx_s,
+                                                  double inv_h, double h, int3 cmin, int3 cmax, int* __restrict__ neighbors) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int self = idx_s[t];
+  const unsigned long long key = keys_s[t];
+  double bd[K];
+  int bi[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) { bd[k] = 1e300; bi[k] = 0x7fffffff; }
+  int cnt = 0;
+  if (key != kKnnInvalid) {
+    const double4 p = pts_s[t];
+    int cx, cy, cz;
+    gb_unpack_key(key, cx, cy, cz);
+    const double ux = p.x * inv_h - (double)cx, uy = p.y * inv_h - (double)cy, uz = p.z * inv_h - (double)cz;  // in [0, 1)
+    // the cube must eventually cover every occupied cell
+    const int rmax = max(max(max(cx - cmin.x, cmax.x - cx), max(cy - cmin.y, cmax.y - cy)), max(cz - cmin.z, cmax.z - cz));
+    for (int r = 0; r <= rmax; r++) {
+      for (int dx = -r; dx <= r; dx++) {
+        const int x = cx + dx;
+        if (x < cmin.x || x > cmax.x) continue;
+        for (int dy = -r; dy <= r; dy++) {
+          const int y = cy + dy;
+          if (y < cmin.y || y > cmax.y) continue;
+          const bool edge = (abs(dx) == r) || (abs(dy) == r);
+          // edge columns contribute their whole z range; interior columns only the two new cells at z = cz -+ r
+          const int nseg = edge ? 1 : 2;
+          for (int sgi = 0; sgi < nseg; sgi++) {
+            int z0, z1;
+            if (edge) { z0 = cz - r; z1 = cz + r; } else { z0 = z1 = (sgi == 0) ? cz - r : cz + r; }
+            z0 = max(z0, cmin.z); z1 = min(z1, cmax.z);
+            if (z0 > z1) continue;
+            unsigned long long klo, khi;
+            gb_pack_key(x, y, z0, &klo);
+            gb_pack_key(x, y, z1, &khi);
+            for (int s = knn_lower_bound(keys_s, n, klo); s < n; s++) {
+              if (__ldg(&keys_s[s]) > khi) break;
+              const double4 q = pts_s[s];
+              const double ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+              const double d = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+              const int j = __ldg(&idx_s[s]);
+              if (d < bd[K - 1] || (d == bd[K - 1] && j < bi[K - 1])) {
+                double cd = d;
+                int ci = j;
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                  if (cd < bd[k] || (cd == bd[k] && ci < bi[k])) {
+                    const double td = bd[k]; const int ti = bi[k];
+                    bd[k] = cd; bi[k] = ci; cd = td; ci = ti;
+                  }
+                }
+                cnt++;
+              }
+            }
+          }
+        }
+      }
+      if (cnt >= K) {
+        const double m = fmin(fmin(fmin(ux, 1.0 - ux), fmin(uy, 1.0 - uy)), fmin(uz, 1.0 - uz)) + (double)r;
+        const double bound = m * h * (1.0 - 1e-12);
+        if (bd[K - 1] <= bound * bound) break;
+      }
+    }
+  }
+  const int found = min(cnt, K);
+#pragma unroll
+  for (int k = 0; k < K; k++) neighbors[(size_t)self * K + k] = k < found ? bi[k] : self;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -244,19 +366,79 @@ __global__ void k_grid_means(int V, const int* __restrict__ starts, const int* _
 
 }  // namespace
 
+template <int K>
+static void launch_knn(bool grid, int n, const double4* d_pts, const double4* d_pts_s, const unsigned long long* d_keys_s, const int* d_idx_s, double inv_h, double h, int3 cmin, int3 cmax, int* d_nb, cudaStream_t st) {
+  const int tb = 128, gb = (n + tb - 1) / tb;
+  if (grid) k_knn_grid<K><<<gb, tb, 0, st>>>(n, d_pts_s, d_keys_s, d_idx_s, inv_h, h, cmin, cmax, d_nb);
+  else k_knn_bruteforce<K><<<gb, tb, 0, st>>>(n, d_pts, d_nb);
+}
+
 gb_status gb_find_neighbors_impl(gb_ctx* ctx, size_t n_, const double* xyzw, int k, int32_t* neighbors) {
   const int n = (int)n_;
   if (n == 0) return GB_OK;
   cudaStream_t st = ctx->stream;
+  const char* mode = getenv("GB_KNN");
+  const bool grid = mode ? (strcmp(mode, "grid") == 0) : (n >= 4096);
+  size_t cub_sort = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_sort, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, n, 0, 64, st);
   const size_t pts_b = align_up(sizeof(double4) * (size_t)n, 256), nb_b = align_up(sizeof(int) * (size_t)n * k, 256);
+  const size_t key_b = align_up(sizeof(unsigned long long) * (size_t)n, 256), idx_b = align_up(sizeof(int) * (size_t)n, 256), cub_b = align_up(cub_sort, 256);
   char* base = nullptr;
-  GB_CHECK(gb_ctx_scratch(ctx, pts_b + nb_b, (void**)&base));
-  double4* d_pts = (double4*)base;
-  int* d_nb = (int*)(base + pts_b);
+  GB_CHECK(gb_ctx_scratch(ctx, 2 * pts_b + nb_b + 2 * key_b + 2 * idx_b + cub_b + 256, (void**)&base));
+  char* p = base;
+  double4* d_pts = (double4*)p; p += pts_b;
+  double4* d_pts_s = (double4*)p; p += pts_b;
+  int* d_nb = (int*)p; p += nb_b;
+  unsigned long long* d_keys = (unsigned long long*)p; p += key_b;
+  unsigned long long* d_keys_s = (unsigned long long*)p; p += key_b;
+  int* d_idx = (int*)p; p += idx_b;
+  int* d_idx_s = (int*)p; p += idx_b;
+  void* d_cub = p; p += cub_b;
+  int* d_count = (int*)p;
   GB_CUDA(cudaMemcpyAsync(d_pts, xyzw, sizeof(double4) * (size_t)n, cudaMemcpyHostToDevice, st));
-  const int tb = 128, gb = (n + tb - 1) / tb;
+  double h = 0.25, inv_h = 4.0;
+  int3 cmin = make_int3(0, 0, 0), cmax = make_int3(0, 0, 0);
+  if (grid) {
+    const int tb = 256, gb = (n + tb - 1) / tb;
+    // cell size: measure the occupancy at 0.25 m, then aim for ~4 points per occupied cell (points lie on surfaces:
+    // points per cell grows with h^2); a second pass re-sorts at the chosen size
+    for (int pass = 0; pass < 2; pass++) {
+      inv_h = 1.0 / h;
+      k_knn_keys<<<gb, tb, 0, st>>>(n, d_pts, inv_h, d_keys, d_idx);
+      size_t tmp = cub_b;
+      GB_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, tmp, d_keys, d_keys_s, d_idx, d_idx_s, n, 0, 64, st));
+      ctx->launches += 2;
+      if (pass == 1) break;
+      int occ = 0;
+      GB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), st));
+      k_count_heads<<<gb, tb, 0, st>>>(n, d_keys_s, d_count);
+      GB_CUDA(cudaMemcpyAsync(&occ, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+      GB_CUDA(cudaStreamSynchronize(st));
+      ctx->launches++;
+      const double per_cell = occ > 0 ? (double)n / occ : 1.0;
+      double h2 = h * sqrt(4.0 / per_cell);
+      h2 = fmin(4.0, fmax(0.02, h2));
+      if (fabs(h2 - h) < 0.1 * h) break;  // close enough: keep the first sort
+      h = h2;
+    }
+    inv_h = 1.0 / h;
+    k_knn_gather<<<gb, tb, 0, st>>>(n, d_idx_s, d_pts, d_pts_s);
+    ctx->launches++;
+    // bounding box of the occupied cells (host: one pass over the caller's array, same floor(p * inv_h) as the kernel)
+    bool any = false;
+    for (int i = 0; i < n; i++) {
+      const double* q = xyzw + 4 * (size_t)i;
+      if (!(std::isfinite(q[0]) && std::isfinite(q[1]) && std::isfinite(q[2]))) continue;
+      const double fx = floor(q[0] * inv_h), fy = floor(q[1] * inv_h), fz = floor(q[2] * inv_h);
+      if (!(fabs(fx) < 1048575.0 && fabs(fy) < 1048575.0 && fabs(fz) < 1048575.0)) continue;
+      const int x = (int)fx, y = (int)fy, z = (int)fz;
+      if (!any) { cmin = cmax = make_int3(x, y, z); any = true; }
+      cmin.x = std::min(cmin.x, x); cmin.y = std::min(cmin.y, y); cmin.z = std::min(cmin.z, z);
+      cmax.x = std::max(cmax.x, x); cmax.y = std::max(cmax.y, y); cmax.z = std::max(cmax.z, z);
+    }
+  }
   switch (k) {
-#define GB_KNN_CASE(K) case K: k_knn_bruteforce<K><<<gb, tb, 0, st>>>(n, d_pts, d_nb); break;
+#define GB_KNN_CASE(K) case K: launch_knn<K>(grid, n, d_pts, d_pts_s, d_keys_s, d_idx_s, inv_h, h, cmin, cmax, d_nb, st); break;
     GB_KNN_CASE(1) GB_KNN_CASE(2) GB_KNN_CASE(3) GB_KNN_CASE(4) GB_KNN_CASE(5) GB_KNN_CASE(6) GB_KNN_CASE(7) GB_KNN_CASE(8)
     GB_KNN_CASE(9) GB_KNN_CASE(10) GB_KNN_CASE(12) GB_KNN_CASE(15) GB_KNN_CASE(16) GB_KNN_CASE(20) GB_KNN_CASE(24) GB_KNN_CASE(32)
 #undef GB_KNN_CASE

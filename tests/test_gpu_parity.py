@@ -270,6 +270,29 @@ def test_find_neighbors_matches_oracle(ctx):
     assert (nb[:, 4:] == np.arange(4)[:, None]).all()
 
 
+def test_grid_knn_is_exact(ctx, monkeypatch):
+    """The uniform-grid k-NN (default for >= 4096 points) returns exactly the oracle's indices: same distances, same tie rule,
+    on a dense small cloud, a cloud with duplicated points and far outliers, and a full 60 k-point scan."""
+    from glim_b200 import preprocess
+
+    monkeypatch.setenv("GB_KNN", "grid")
+    P = util.scan_pair(n_rays=32 * 100)["points"][0]
+    rng = synth.rng_for(31)
+    dup = np.concatenate([P[:500], P[:500], P[100:200] + [1e-9, 0, 0, 0], [[500.0, -300.0, 20.0, 1.0], [-800.0, 10.0, 5.0, 1.0]], rng.normal(0, 0.01, (64, 4)) * [1, 1, 1, 0] + [3, 3, 3, 1]])
+    for cloud in (P, dup, P[:7]):
+        for k in (10, 5):
+            nb = preprocess.find_neighbors(cloud, k, ctx=ctx).reshape(len(cloud), k)
+            ref, _ = oracle.knn_bruteforce(cloud, k)
+            assert np.array_equal(nb, ref)
+    monkeypatch.delenv("GB_KNN")
+    sc = synth.make_hall_scene()
+    big, _ = synth.scan(sc, "hdl32", synth.arc_trajectory(8)[2], synth.rng_for(32))
+    assert len(big) == 60000
+    nb = preprocess.find_neighbors(big, 10, ctx=ctx).reshape(-1, 10)
+    ref, _ = oracle.knn_bruteforce(big, 10)
+    assert np.array_equal(nb, ref)
+
+
 def test_voxelgrid_sampling_matches_oracle(ctx, pair):
     from glim_b200 import preprocess
 
