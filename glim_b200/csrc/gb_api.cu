@@ -350,18 +350,12 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   const int capacity = ctx->num_sms * ctas_per_sm;
   int tile = env_int("GB_TILE", 0);
   if (tile <= 0) {
-    // work items are per WARP.  Large sweeps: ~6 items per warp drawn dynamically, at most 2048 points each (measured
-    // optimum on B200 across the BASELINE workloads, profiles/tune_sweep_r01.txt).  Small sweeps (an odometry frame, a
-    // single pair) are latency-bound: as many warps as possible must have work, so items shrink down to 32 points
-    // (~1.5 items per warp; fewer, larger items were measured slower).
+    // work items are per WARP: ~6 items per warp drawn dynamically, between 128 and 2048 points each (measured optimum on
+    // B200 across the BASELINE workloads, profiles/tune_sweep_r01.txt; for small sweeps both more-and-smaller and
+    // fewer-and-larger items were measured slower than 128-point items)
     const uint64_t warps = (uint64_t)capacity * 8;
-    const uint64_t per_warp = (total_pts + warps - 1) / warps;
-    if (per_warp < 192) {
-      tile = (int)std::max<uint64_t>(32, (per_warp * 2 / 3 + 31) / 32 * 32);
-    } else {
-      const uint64_t want = total_pts / (warps * 6) + 1;
-      tile = (int)std::min<uint64_t>(2048, std::max<uint64_t>(128, (want + 31) / 32 * 32));
-    }
+    const uint64_t want = total_pts / (warps * 6) + 1;
+    tile = (int)std::min<uint64_t>(2048, std::max<uint64_t>(128, (want + 31) / 32 * 32));
   }
   tile = std::min(1 << 20, std::max(32, (tile + 31) / 32 * 32));
   s->tile_size = tile;

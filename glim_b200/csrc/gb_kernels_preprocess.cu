@@ -138,7 +138,12 @@ __global__ void __launch_bounds__(128) k_knn_grid(int n, const double4* __restri
     const double ux = p.x * inv_h - (double)cx, uy = p.y * inv_h - (double)cy, uz = p.z * inv_h - (double)cz;  // in [0, 1)
     // the cube must eventually cover every occupied cell
     const int rmax = max(max(max(cx - cmin.x, cmax.x - cx), max(cy - cmin.y, cmax.y - cy)), max(cz - cmin.z, cmax.z - cz));
-    for (int r = 0; r <= rmax; r++) {
+    // ring r costs (2r+1)^2 range searches: an isolated point (a far return with no neighbours nearby) would walk thousands of
+    // empty rings.  After kMaxRing rings without a proof of completeness the query falls back to a scan of ALL points
+    // (exact, O(N), only for the few isolated queries).
+    constexpr int kMaxRing = 6;
+    bool complete = false;
+    for (int r = 0; r <= min(rmax, kMaxRing); r++) {
       for (int dx = -r; dx <= r; dx++) {
         const int x = cx + dx;
         if (x < cmin.x || x > cmax.x) continue;
@@ -178,10 +183,35 @@ __global__ void __launch_bounds__(128) k_knn_grid(int n, const double4* __restri
           }
         }
       }
+      if (r == rmax) { complete = true; break; }  // the cube covers every occupied cell
       if (cnt >= K) {
         const double m = fmin(fmin(fmin(ux, 1.0 - ux), fmin(uy, 1.0 - uy)), fmin(uz, 1.0 - uz)) + (double)r;
         const double bound = m * h * (1.0 - 1e-12);
-        if (bd[K - 1] <= bound * bound) break;
+        if (bd[K - 1] <= bound * bound) { complete = true; break; }
+      }
+    }
+    if (!complete) {
+#pragma unroll
+      for (int k = 0; k < K; k++) { bd[k] = 1e300; bi[k] = 0x7fffffff; }
+      cnt = 0;
+      for (int s = 0; s < n; s++) {
+        if (__ldg(&keys_s[s]) == kKnnInvalid) break;  // invalid points sort last
+        const double4 q = pts_s[s];
+        const double ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+        const double d = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+        const int j = __ldg(&idx_s[s]);
+        if (d < bd[K - 1] || (d == bd[K - 1] && j < bi[K - 1])) {
+          double cd = d;
+          int ci = j;
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            if (cd < bd[k] || (cd == bd[k] && ci < bi[k])) {
+              const double td = bd[k]; const int ti = bi[k];
+              bd[k] = cd; bi[k] = ci; cd = td; ci = ti;
+            }
+          }
+          cnt++;
+        }
       }
     }
   }
