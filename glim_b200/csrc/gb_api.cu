@@ -389,11 +389,15 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   }
   s->num_tiles = (int)tiles.size();
   s->grid = std::max(1, std::min((s->num_tiles + 7) / 8, capacity));
+  // ~64 items per accumulator copy: sweeps with few factors (an odometry frame, a single pair) would otherwise
+  // serialise hundreds of fp64 atomics on the same addresses
+  s->acc_slots = 1;
+  while (F > 0 && s->acc_slots < 16 && (uint64_t)s->num_tiles > (uint64_t)F * 64 * s->acc_slots) s->acc_slots *= 2;
 
   if (F > 0) {
     // one device allocation, one pinned allocation
     const size_t b_desc = align_up(sizeof(FactorDesc) * F, 256), b_tiles = align_up(sizeof(int2) * tiles.size(), 256), b_pose = align_up(sizeof(double) * 16 * F, 256);
-    const size_t b_acc = align_up(sizeof(double) * GB_ACC_STRIDE * F, 256), b_done = align_up(sizeof(unsigned) * F + 16, 256), b_out = align_up(sizeof(double) * GB_OUT_DOUBLES * F, 256);
+    const size_t b_acc = align_up(sizeof(double) * GB_ACC_STRIDE * F * s->acc_slots, 256), b_done = align_up(sizeof(unsigned) * F + 16, 256), b_out = align_up(sizeof(double) * GB_OUT_DOUBLES * F, 256);
     const size_t total = b_desc + b_tiles + 2 * b_pose + b_acc + b_done + b_out;
     char* d = nullptr;
     cudaError_t e = cudaMalloc((void**)&d, total);

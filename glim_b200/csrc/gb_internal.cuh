@@ -131,7 +131,8 @@ struct gb_sweep {
   int2* d_tiles;          // {factor, begin}
   double* d_poses;        // F x 16 (T_lin)
   double* d_poses_eval;   // F x 16 (error mode)
-  double* d_accum;        // F x GB_ACC_STRIDE, zero between sweeps (self-cleaning)
+  double* d_accum;        // F x acc_slots x GB_ACC_STRIDE, zero between sweeps (self-cleaning)
+  int acc_slots;          // power of two: copies of each factor's accumulator (spreads same-address atomics of few-factor sweeps)
   unsigned* d_done;       // F tickets, zero between sweeps
   unsigned long long* d_tile_ctr;  // dynamic tile queue head, monotonic across launches
   unsigned long long ctr_base;     // value of the counter at the start of the next launch

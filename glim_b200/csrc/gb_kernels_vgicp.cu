@@ -145,17 +145,25 @@ __device__ void pair_push(int f, const FactorDesc& D, const double* __restrict__
   (void)f;
 }
 
-__device__ void factor_epilogue(int f, const FactorDesc& D, const double* __restrict__ poses, double* __restrict__ accum, double* __restrict__ out, float* __restrict__ slab, double* sm /* >= 36+36+36+32 doubles */) {
+__device__ void factor_epilogue(int f, const FactorDesc& D, const double* __restrict__ poses, double* __restrict__ accum, int acc_slots, double* __restrict__ out, float* __restrict__ slab, double* sm /* >= 36+36+36+32 doubles */) {
   const int lane = threadIdx.x & 31;
   double* A = sm;            // 32 accumulators
   double* H = sm + 32;       // 6x6 H_tt, row-major (symmetric)
   double* Ad = sm + 68;      // 6x6 adjoint, row-major
   double* X = sm + 104;      // H_tt * Ad, row-major
   // the accumulators were produced by L2 atomics of other CTAs: read them past L1
-  if (lane < 29) A[lane] = __ldcg(&accum[(size_t)f * GB_ACC_STRIDE + lane]);
+  // (a factor's accumulator is replicated over acc_slots copies so that the items of a sweep with FEW factors do not all
+  //  serialise on the same 29 addresses in L2; summed here in slot order)
+  if (lane < 29) {
+    double a = 0.0;
+    for (int sl = 0; sl < acc_slots; sl++) {
+      double* slot = &accum[((size_t)f * acc_slots + sl) * GB_ACC_STRIDE + lane];
+      a += __ldcg(slot);
+      *slot = 0.0;  // re-zero for the next sweep (self-cleaning; nobody touches this factor again in this launch)
+    }
+    A[lane] = a;
+  }
   __syncwarp();
-  // re-zero for the next sweep (self-cleaning; nobody touches this factor again in this launch)
-  if (lane < 29) accum[(size_t)f * GB_ACC_STRIDE + lane] = 0.0;
   // unpack upper triangle
   if (lane == 0) {
     int k = 0;
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
   const FactorDesc* __restrict__ descs, const double* __restrict__ poses, const double* __restrict__ poses_eval,
   const int2* __restrict__ items, int num_items, int chunk,
   unsigned long long* __restrict__ item_ctr, unsigned long long ctr_base,
-  double* __restrict__ accum, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab, const PeerPush peer) {
+  double* __restrict__ accum, int acc_slots, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab, const PeerPush peer) {
   __shared__ __align__(16) uint2 s_q[kWarps][kSubMax];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -369,15 +377,16 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
     }
 
     // ---------------- item reduction: warp -> 29 fp64 atomics ----------------
+    double* __restrict__ my_acc = accum + ((size_t)f * acc_slots + (size_t)(item & (acc_slots - 1))) * GB_ACC_STRIDE;
     if (MODE == GB_MODE_LINEARIZE) {
       const float r = warp_reduce_scatter32(acc, lane);
-      if (lane < 29) atomicAdd(&accum[(size_t)f * GB_ACC_STRIDE + lane], (double)r);
+      if (lane < 29) atomicAdd(&my_acc[lane], (double)r);
     } else {
       float e = acc[27], n = acc[28];
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) { e += __shfl_xor_sync(0xffffffffu, e, o); n += __shfl_xor_sync(0xffffffffu, n, o); }
-      if (lane == 27) atomicAdd(&accum[(size_t)f * GB_ACC_STRIDE + 27], (double)e);
-      if (lane == 28) atomicAdd(&accum[(size_t)f * GB_ACC_STRIDE + 28], (double)n);
+      if (lane == 27) atomicAdd(&my_acc[27], (double)e);
+      if (lane == 28) atomicAdd(&my_acc[28], (double)n);
     }
     __threadfence();
     __syncwarp();
@@ -390,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
     last = __shfl_sync(0xffffffffu, last, 0);
     if (last) {
       __threadfence();
-      factor_epilogue(f, D, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, out, slab, reinterpret_cast<double*>(q));
+      factor_epilogue(f, D, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, acc_slots, out, slab, reinterpret_cast<double*>(q));
       __syncwarp();
       if (MODE == GB_MODE_LINEARIZE && peer.world > 0) pair_push(f, D, out, peer, reinterpret_cast<float*>(q) + 512);
       __syncwarp();
@@ -438,7 +447,7 @@ static void launch_variant(gb_sweep* s, const double* poses_eval, float* slab) {
     for (int p = 0; p < ps->world; p++) pp.base[p] = reinterpret_cast<float*>(ps->peer[p]) + (size_t)ps->parity * ps->buf_floats;
     pp.pair_ptr = s->d_pair_ptr; pp.pair_factors = s->d_pair_factors; pp.pair_done = s->d_pair_done;
   }
-  k_vgicp_sweep<MODE, MINB><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->d_done, s->d_out, slab, pp);
+  k_vgicp_sweep<MODE, MINB><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
 }
 
 // completion flags of the fused exchange: one thread per rank publishes this rank's step to that peer, then waits for the
