@@ -346,6 +346,7 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     total_pts += factors[f]->source->n;
   }
   s->min_blocks = std::min(4, std::max(2, env_int("GB_MIN_BLOCKS", 2)));
+  s->static_first = env_int("GB_STATIC_FIRST", 1);
   const int ctas_per_sm = env_int("GB_CTAS_PER_SM", s->min_blocks);
   const int capacity = ctx->num_sms * ctas_per_sm;
   int tile = env_int("GB_TILE", 0);

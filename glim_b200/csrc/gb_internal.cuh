@@ -149,6 +149,7 @@ struct gb_sweep {
   std::vector<int> h_pair;        // pair id per factor
   int num_tiles, tile_size, grid;   // work items, points per item, CTAs
   int min_blocks;                   // kernel register-budget variant (CTAs per SM)
+  int static_first;                 // first item of a warp = its index (1) or drawn from the queue (0)
   uint64_t point_factors, algorithmic_bytes;
   uint64_t key;           // cache key
   uint64_t epoch;

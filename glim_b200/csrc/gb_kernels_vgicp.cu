@@ -251,7 +251,7 @@ __device__ __forceinline__ PoseF pose_from_colmajor(const double* __restrict__ T
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
   const FactorDesc* __restrict__ descs, const double* __restrict__ poses, const double* __restrict__ poses_eval,
-  const int2* __restrict__ items, int num_items, int chunk,
+  const int2* __restrict__ items, int num_items, int chunk, int static_first,
   unsigned long long* __restrict__ item_ctr, unsigned long long ctr_base,
   double* __restrict__ accum, int acc_slots, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab, const PeerPush peer) {
   __shared__ __align__(16) uint2 s_q[kWarps][kSubMax];
@@ -261,9 +261,13 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
 
   // first item: static (warp id) -- thousands of warps hammering one atomic at kernel start cost ~10 us, which is most of
   // a small odometry sweep; further items (only when there are more items than warps) come from the global queue
-  const int total_warps = gridDim.x * kWarps;
+  const int total_warps = static_first ? gridDim.x * kWarps : 0;
   const bool dynamic = num_items > total_warps;
   int item = blockIdx.x * kWarps + warp;
+  if (!static_first) {
+    if (lane == 0) item = (int)(atomicAdd(item_ctr, 1ull) - ctr_base);
+    item = __shfl_sync(0xffffffffu, item, 0);
+  }
 
   while (item < num_items) {
     int next_item = 0x7fffffff;
@@ -447,7 +451,7 @@ static void launch_variant(gb_sweep* s, const double* poses_eval, float* slab) {
     for (int p = 0; p < ps->world; p++) pp.base[p] = reinterpret_cast<float*>(ps->peer[p]) + (size_t)ps->parity * ps->buf_floats;
     pp.pair_ptr = s->d_pair_ptr; pp.pair_factors = s->d_pair_factors; pp.pair_done = s->d_pair_done;
   }
-  k_vgicp_sweep<MODE, MINB><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
+  k_vgicp_sweep<MODE, MINB><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->static_first, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
 }
 
 // completion flags of the fused exchange: one thread per rank publishes this rank's step to that peer, then waits for the
@@ -485,7 +489,8 @@ gb_status gb_launch_sweep(gb_sweep* s, int mode) {
   }
   GB_CUDA(cudaGetLastError());
   // every processed item draws exactly one ticket from the queue (when the queue is in use at all)
-  if (s->num_tiles > s->grid * kWarps) s->ctr_base += (unsigned long long)s->num_tiles;
+  if (!s->static_first) s->ctr_base += (unsigned long long)s->num_tiles + (unsigned long long)s->grid * kWarps;
+  else if (s->num_tiles > s->grid * kWarps) s->ctr_base += (unsigned long long)s->num_tiles;
   ctx->launches++;
   return GB_OK;
 }
