@@ -402,10 +402,17 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = my_bytes / max(1, k_launches) / (kernel_ms_per_launch * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch from the committed ncu --set full capture of this workload (1 GPU, full scale only)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if world == 1 and args.scale == 1.0 and args.workload in tj:
+            traffic, traffic_src = tj[args.workload]["dram_bytes_per_launch"], tj[args.workload]["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_vgicp_sweep<LINEARIZE>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": my_bytes / max(1, k_launches), "launch_ms": kernel_ms_per_launch,
-                "traffic": None, "note": "achieved = SURVEY 8(d) B_sweep (48 B per point.factor + 48 B per target voxel + 16 B per bucket + 552 B per factor) / CUDA-event launch time; source clouds shared by consecutive factors are re-read from L2, so DRAM traffic is below B_sweep (see profiles/)"}
+                "traffic": traffic, "traffic_source": traffic_src, "note": "achieved = SURVEY 8(d) B_sweep (48 B per point.factor + 48 B per target voxel + 16 B per bucket + 552 B per factor) / CUDA-event launch time; source clouds shared by consecutive factors are re-read from L2, so DRAM traffic is below B_sweep (see profiles/)"}
 
     # ---- end to end through the C-ABI with host buffers ----
     host_deltas = [sw._sub.deltas.copy() for sw in sweeps]

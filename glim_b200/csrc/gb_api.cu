@@ -336,7 +336,7 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   s->d_descs = nullptr; s->d_tiles = nullptr; s->d_poses = nullptr; s->d_poses_eval = nullptr; s->d_accum = nullptr; s->d_done = nullptr; s->d_out = nullptr;
   s->h_poses = nullptr; s->h_poses_eval = nullptr; s->h_out = nullptr; s->d_slab = nullptr; s->num_pairs = 0;
   s->d_tile_ctr = nullptr; s->ctr_base = 0;
-  s->peer = nullptr; s->d_pair_ptr = nullptr; s->d_pair_factors = nullptr; s->d_pair_done = nullptr;
+  s->peer = nullptr; s->d_pair_ptr = nullptr; s->d_pair_factors = nullptr; s->d_pair_done = nullptr; s->d_peer_tables = nullptr;
   s->num_tiles = 0; s->point_factors = 0; s->algorithmic_bytes = 0; s->key = 0; s->epoch = ctx->epoch;
 
   // tile size: enough tiles to balance the persistent grid, large enough to amortise the per-tile reduction
@@ -628,6 +628,7 @@ extern "C" gb_status gb_sweep_attach_peer_slab(gb_sweep* s, gb_peer_slab* ps) {
   GB_REQUIRE(s, "null sweep");
   if (!ps) { s->peer = nullptr; return GB_OK; }
   GB_REQUIRE(ps->ctx == s->ctx, "peer slab belongs to another context");
+  GB_REQUIRE(ps->connected, "connect the peer slab (gb_peer_slab_connect) before attaching it");
   // CSR: global pair id -> this sweep's factor indices
   const size_t P = ps->num_pairs;
   std::vector<int> ptr(P + 1, 0), fac(s->F);
@@ -643,8 +644,17 @@ extern "C" gb_status gb_sweep_attach_peer_slab(gb_sweep* s, gb_peer_slab* ps) {
   if (s->d_pair_ptr) { GB_CUDA(cudaFree(s->d_pair_ptr)); s->d_pair_ptr = nullptr; }
   const size_t b_ptr = align_up(sizeof(int) * (P + 1), 256), b_fac = align_up(sizeof(int) * std::max<size_t>(1, s->F), 256), b_done = align_up(sizeof(unsigned) * P, 256);
   char* d = nullptr;
-  GB_CUDA(cudaMalloc((void**)&d, b_ptr + b_fac + b_done));
+  GB_CUDA(cudaMalloc((void**)&d, b_ptr + b_fac + b_done + 2 * sizeof(PeerPush)));
   s->d_pair_ptr = (int*)d; s->d_pair_factors = (int*)(d + b_ptr); s->d_pair_done = (unsigned*)(d + b_ptr + b_fac);
+  s->d_peer_tables = (PeerPush*)(d + b_ptr + b_fac + b_done);
+  PeerPush tabs[2];
+  memset(tabs, 0, sizeof(tabs));
+  for (int par = 0; par < 2; par++) {
+    tabs[par].world = ps->world;
+    for (int p = 0; p < ps->world; p++) tabs[par].base[p] = reinterpret_cast<float*>(ps->peer[p]) + (size_t)par * ps->buf_floats;
+    tabs[par].pair_ptr = s->d_pair_ptr; tabs[par].pair_factors = s->d_pair_factors; tabs[par].pair_done = s->d_pair_done;
+  }
+  GB_CUDA(cudaMemcpy(s->d_peer_tables, tabs, sizeof(tabs), cudaMemcpyHostToDevice));
   GB_CUDA(cudaMemcpy(s->d_pair_ptr, ptr.data(), sizeof(int) * (P + 1), cudaMemcpyHostToDevice));
   if (s->F) GB_CUDA(cudaMemcpy(s->d_pair_factors, fac.data(), sizeof(int) * s->F, cudaMemcpyHostToDevice));
   GB_CUDA(cudaMemset(s->d_pair_done, 0, b_done));

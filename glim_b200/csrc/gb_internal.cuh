@@ -95,7 +95,7 @@ struct gb_factor {
 };
 
 #define GB_MAX_PEERS 8
-// by-value kernel parameter of the fused result exchange
+// device-resident parameter block of the fused result exchange (one per step parity)
 struct PeerPush {
   int world;                      // 0 = disabled
   float* base[GB_MAX_PEERS];      // every rank's slab buffer of the current step parity, as mapped on THIS device
@@ -146,6 +146,7 @@ struct gb_sweep {
   int* d_pair_ptr;                // CSR pair -> factors (device), built when a peer slab is attached
   int* d_pair_factors;
   unsigned* d_pair_done;
+  PeerPush* d_peer_tables;        // [2]: one per step parity
   std::vector<int> h_pair;        // pair id per factor
   int num_tiles, tile_size, grid;   // work items, points per item, CTAs
   int min_blocks;                   // kernel register-budget variant (CTAs per SM)

@@ -139,9 +139,9 @@ __global__ void __launch_bounds__(128) k_knn_grid(int n, const double4* __restri
     // the cube must eventually cover every occupied cell
     const int rmax = max(max(max(cx - cmin.x, cmax.x - cx), max(cy - cmin.y, cmax.y - cy)), max(cz - cmin.z, cmax.z - cz));
     // ring r costs (2r+1)^2 range searches: an isolated point (a far return with no neighbours nearby) would walk thousands of
-    // empty rings.  After kMaxRing rings without a proof of completeness the query falls back to a scan of ALL points
+    // empty rings.  After kMaxRing rings (~6.5 k range searches) without a proof of completeness the query falls back to a scan of ALL points
     // (exact, O(N), only for the few isolated queries).
-    constexpr int kMaxRing = 6;
+    constexpr int kMaxRing = 16;
     bool complete = false;
     for (int r = 0; r <= min(rmax, kMaxRing); r++) {
       for (int dx = -r; dx <= r; dx++) {

@@ -115,7 +115,8 @@ __device__ __forceinline__ int slab_to_record(int e) {
 // Fused result exchange: executed by the warp that completed factor f.  If f was the LAST factor of its pair, sum the
 // pair's records (fp64, fixed order -> deterministic), and store the fp32 row into every rank's slab (128-bit stores;
 // peers are reached through their IPC-mapped addresses over NVLink).
-__device__ void pair_push(int f, const FactorDesc& D, const double* __restrict__ out, const PeerPush& peer, float* row /* 96 floats of shared memory */) {
+__device__ __noinline__ void pair_push(int f, const FactorDesc& D, const double* __restrict__ out, const PeerPush* __restrict__ peer_tab, float* row /* 96 floats of shared memory */) {
+  const PeerPush& peer = *peer_tab;
   const int lane = threadIdx.x & 31;
   __threadfence();  // this factor's record is visible before the ticket
   __syncwarp();
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
   const FactorDesc* __restrict__ descs, const double* __restrict__ poses, const double* __restrict__ poses_eval,
   const int2* __restrict__ items, int num_items, int chunk, int static_first,
   unsigned long long* __restrict__ item_ctr, unsigned long long ctr_base,
-  double* __restrict__ accum, int acc_slots, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab, const PeerPush peer) {
+  double* __restrict__ accum, int acc_slots, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab, const PeerPush* __restrict__ peer) {
   __shared__ __align__(16) uint2 s_q[kWarps][kSubMax];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
       __threadfence();
       factor_epilogue(f, D, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, acc_slots, out, slab, reinterpret_cast<double*>(q));
       __syncwarp();
-      if (MODE == GB_MODE_LINEARIZE && peer.world > 0) pair_push(f, D, out, peer, reinterpret_cast<float*>(q) + 512);
+      if (MODE == GB_MODE_LINEARIZE && peer != nullptr) pair_push(f, D, out, peer, reinterpret_cast<float*>(q) + 512);
       __syncwarp();
     }
     item = __shfl_sync(0xffffffffu, next_item, 0);
@@ -443,14 +444,8 @@ __global__ void __launch_bounds__(256) k_overlap(int num_targets, const FactorDe
 
 template <int MODE, int MINB>
 static void launch_variant(gb_sweep* s, const double* poses_eval, float* slab) {
-  PeerPush pp;
-  memset(&pp, 0, sizeof(pp));
-  if (MODE == GB_MODE_LINEARIZE && s->peer) {
-    gb_peer_slab* ps = s->peer;
-    pp.world = ps->world;
-    for (int p = 0; p < ps->world; p++) pp.base[p] = reinterpret_cast<float*>(ps->peer[p]) + (size_t)ps->parity * ps->buf_floats;
-    pp.pair_ptr = s->d_pair_ptr; pp.pair_factors = s->d_pair_factors; pp.pair_done = s->d_pair_done;
-  }
+  // the table for the buffer of the current step parity (both were written to the device when the slab was attached)
+  const PeerPush* pp = (MODE == GB_MODE_LINEARIZE && s->peer) ? s->d_peer_tables + s->peer->parity : nullptr;
   k_vgicp_sweep<MODE, MINB><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->static_first, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
 }
 
