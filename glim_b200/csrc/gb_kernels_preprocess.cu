@@ -121,7 +121,7 @@ __device__ __forceinline__ int knn_lower_bound(const unsigned long long* __restr
 
 template <int K>
 __global__ void __launch_bounds__(128) k_knn_grid(int n, const double4* __restrict__ pts_s, const unsigned long long* __restrict__ keys_s, const int* __restrict__ idx_s,
-                                                  double inv_h, double h, int3 cmin, int3 cmax, int* __restrict__ neighbors) {
+                                                  double inv_h, double h, int3 cmin, int3 cmax, int max_ring, int* __restrict__ neighbors) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int self = idx_s[t];
@@ -139,11 +139,10 @@ __global__ void __launch_bounds__(128) k_knn_grid(int n, const double4* __restri
     // the cube must eventually cover every occupied cell
     const int rmax = max(max(max(cx - cmin.x, cmax.x - cx), max(cy - cmin.y, cmax.y - cy)), max(cz - cmin.z, cmax.z - cz));
     // ring r costs (2r+1)^2 range searches: an isolated point (a far return with no neighbours nearby) would walk thousands of
-    // empty rings.  After kMaxRing rings (~6.5 k range searches) without a proof of completeness the query falls back to a scan of ALL points
-    // (exact, O(N), only for the few isolated queries).
-    constexpr int kMaxRing = 16;
+    // empty rings.  After max_ring rings (chosen on the host so that the ring walk costs about as much as one pass over all
+    // points) without a proof of completeness the query falls back to a scan of ALL points (exact, O(N)).
     bool complete = false;
-    for (int r = 0; r <= min(rmax, kMaxRing); r++) {
+    for (int r = 0; r <= min(rmax, max_ring); r++) {
       for (int dx = -r; dx <= r; dx++) {
         const int x = cx + dx;
         if (x < cmin.x || x > cmax.x) continue;
@@ -399,7 +398,9 @@ __global__ void k_grid_means(int V, const int* __restrict__ starts, const int* _
 template <int K>
 static void launch_knn(bool grid, int n, const double4* d_pts, const double4* d_pts_s, const unsigned long long* d_keys_s, const int* d_idx_s, double inv_h, double h, int3 cmin, int3 cmax, int* d_nb, cudaStream_t st) {
   const int tb = 128, gb = (n + tb - 1) / tb;
-  if (grid) k_knn_grid<K><<<gb, tb, 0, st>>>(n, d_pts_s, d_keys_s, d_idx_s, inv_h, h, cmin, cmax, d_nb);
+  // (4/3) R^3 range searches of log2(n) steps each ~ n  =>  R = cbrt(0.75 n / log2 n)
+  const int max_ring = std::min(64, std::max(6, (int)cbrt(0.75 * (double)n / std::max(1.0, log2((double)n)))));
+  if (grid) k_knn_grid<K><<<gb, tb, 0, st>>>(n, d_pts_s, d_keys_s, d_idx_s, inv_h, h, cmin, cmax, max_ring, d_nb);
   else k_knn_bruteforce<K><<<gb, tb, 0, st>>>(n, d_pts, d_nb);
 }
 
