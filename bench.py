@@ -295,32 +295,59 @@ def main():
         dist.all_gather(outs, t)
         return [bytes(o.cpu().numpy().tobytes()) for o in outs]
 
-    sweeps, slabs, peers, my_pf, my_bytes, all_pf = [], [], [], 0, 0, 0
-    for fset in w.sets:
-        if sharded:
-            f_rank, _ = multi_gpu.shard_factors(fset.factors, sizes, world, pair_cost=w.notes.get("_pair_overlap"))
-            mine = [k for k in range(len(fset.factors)) if f_rank[k] == rank]
-        else:
-            mine = list(range(len(fset.factors)))
-        sub = type(fset)([fset.factors[k] for k in mine], fset.deltas[mine] if len(mine) else np.zeros((0, 4, 4)))
-        gf = w.gpu_factors(sub)
-        num_pairs = max((f.pair for f in fset.factors), default=-1) + 1
-        sw = gpu.Sweep(ctx, gf, pair_index=[f.pair for f in sub.factors])
-        slab = torch.zeros((max(1, num_pairs), GB_SLAB_STRIDE), dtype=torch.float32, device=f"cuda:{local_rank}")
-        if fused:
-            ps = gpu.PeerSlab(ctx, max(1, num_pairs), world if sharded else 1, rank if sharded else 0, exchange)
-            sw.attach_peer_slab(ps)
-            peers.append(ps)
-        else:
-            sw.attach_slab(slab.data_ptr(), max(1, num_pairs))
-            peers.append(None)
-        sw.set_poses(sub.deltas)
-        sw._sub = sub
-        sweeps.append(sw)
-        slabs.append(slab)
-        my_pf += sw.point_factors
-        my_bytes += sw.algorithmic_bytes
-        all_pf += sum(sizes[f.source] for f in fset.factors)
+    def make_sweeps(inliers_by_set=None, reuse_peers=None):
+        """Partition every factor set over the ranks and prepare this rank's sweeps.  inliers_by_set: measured inlier counts per
+        factor (from a calibration sweep) for the cost-balanced partition; None -> the overlap estimate of the gate."""
+        sweeps, slabs, peers, my_pf, my_bytes, all_pf = [], [], [], 0, 0, 0
+        for si, fset in enumerate(w.sets):
+            if sharded:
+                f_rank, _ = multi_gpu.shard_factors(fset.factors, sizes, world, pair_cost=w.notes.get("_pair_overlap"),
+                                                    factor_inliers=None if inliers_by_set is None else inliers_by_set[si])
+                mine = [k for k in range(len(fset.factors)) if f_rank[k] == rank]
+            else:
+                mine = list(range(len(fset.factors)))
+            sub = type(fset)([fset.factors[k] for k in mine], fset.deltas[mine] if len(mine) else np.zeros((0, 4, 4)))
+            gf = w.gpu_factors(sub)
+            num_pairs = max((f.pair for f in fset.factors), default=-1) + 1
+            sw = gpu.Sweep(ctx, gf, pair_index=[f.pair for f in sub.factors])
+            slab = torch.zeros((max(1, num_pairs), GB_SLAB_STRIDE), dtype=torch.float32, device=f"cuda:{local_rank}")
+            if fused:
+                ps = reuse_peers[si] if reuse_peers is not None else gpu.PeerSlab(ctx, max(1, num_pairs), world if sharded else 1, rank if sharded else 0, exchange)
+                sw.attach_peer_slab(ps)
+                peers.append(ps)
+            else:
+                sw.attach_slab(slab.data_ptr(), max(1, num_pairs))
+                peers.append(None)
+            sw.set_poses(sub.deltas)
+            sw._sub = sub
+            sw._mine = mine
+            sweeps.append(sw)
+            slabs.append(slab)
+            my_pf += sw.point_factors
+            my_bytes += sw.algorithmic_bytes
+            all_pf += sum(sizes[f.source] for f in fset.factors)
+        return sweeps, slabs, peers, my_pf, my_bytes, all_pf
+
+    sweeps, slabs, peers, my_pf, my_bytes, all_pf = make_sweeps()
+    calibrated = False
+    if sharded and world > 1:
+        # Calibration sweep: a relinearizing back-end knows every factor's inlier count from its previous sweep; use it to
+        # balance the partition by measured cost instead of the gate's overlap estimate, then rebuild this rank's sweeps.
+        inl = []
+        for si, (sw, ps) in enumerate(zip(sweeps, peers)):
+            sw.launch()
+            if fused:
+                ps.signal_wait()
+            rec = sw.fetch()
+            full = torch.zeros(len(w.sets[si].factors), dtype=torch.float64, device=f"cuda:{local_rank}")
+            if len(sw._mine):
+                full[torch.tensor(sw._mine, device=full.device)] = torch.from_numpy(np.ascontiguousarray(rec["num_inliers"])).to(full.device)
+            dist.all_reduce(full, op=dist.ReduceOp.SUM)
+            inl.append(full.cpu().numpy())
+        old = sweeps
+        sweeps, slabs, peers, my_pf, my_bytes, all_pf = make_sweeps(inl, reuse_peers=peers if fused else None)
+        del old
+        calibrated = True
     total_pf = all_pf if sharded else all_pf * world  # replicas: every rank processes the whole stream
     ctx.synchronize()
 
@@ -456,7 +483,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.workload, w, {"parallelism": ((f"pairs sharded over {world} rank(s); finished pair rows of the [{slabs[0].shape[0]} x {GB_SLAB_STRIDE}] fp32 Hessian slab are stored into every rank's buffer by the sweep kernel's epilogue over NVLink (CUDA IPC peer memory) + completion flags; no NCCL in the step" if fused else f"pairs sharded over {world} rank(s), NCCL all-reduce of the [{slabs[0].shape[0]} x {GB_SLAB_STRIDE}] fp32 Hessian slab") if sharded else f"replicas x{world} (single online stream does not shard)"),
-                                                       "tiles_grid_first_sweep": [int(sweeps[0].num_tiles), int(sweeps[0].grid)], "build_seconds": round(build_s, 1), "scale": args.scale}),
+                                                       "tiles_grid_first_sweep": [int(sweeps[0].num_tiles), int(sweeps[0].grid)], "partition": ("contiguous, cost = n_source + 1.25 * measured inliers (calibration sweep)" if calibrated else "contiguous, cost = n_source * (1 + 1.25 * gate overlap)") if sharded else None, "build_seconds": round(build_s, 1), "scale": args.scale}),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ems / e_steps},
             "gpu_launches": int(gpu_launches),
             "clocks": sampler.summary(t0, t1) if sampler else None,

@@ -27,12 +27,15 @@ def lpt_partition(weights, n_parts: int):
     return part
 
 
-def shard_factors(factors, source_sizes, world: int, pair_cost=None, contiguous=True):
+def shard_factors(factors, source_sizes, world: int, pair_cost=None, contiguous=True, factor_inliers=None):
     """factors: objects with .pair and .source, in the order the reference creates them (source-major: all factors of one
     new submap are consecutive, global_mapping.cpp:441-470); -> (rank per factor, rank per pair).  Pairs are kept whole.
 
     pair_cost (optional): pair -> expected inlier fraction (the overlap the gate measured).  In the sweep kernel a hit costs
     ~2.2x a miss (fit to the measured sub-mapping / global-mapping throughputs), so a factor weighs n_source * (1 + 1.25 * overlap).
+
+    factor_inliers (optional): measured inlier count per factor from a previous sweep (a relinearizing back-end has them for
+    free): the weight becomes n_source + 1.25 * inliers, which replaces the overlap estimate.
 
     contiguous=True (default): cut the factor list into `world` consecutive chunks of equal total weight.  Every rank then
     keeps ALL factors of the source clouds it touches, so a source cloud is read from HBM once per rank-sweep and served from
@@ -46,9 +49,12 @@ def shard_factors(factors, source_sizes, world: int, pair_cost=None, contiguous=
             pairs.append(f.pair)
     index = {p: k for k, p in enumerate(pairs)}
     w = np.zeros(len(pairs))
-    for f in factors:
-        c = 1.0 + 1.25 * float(pair_cost[f.pair]) if pair_cost is not None and f.pair in pair_cost else 1.0
-        w[index[f.pair]] += source_sizes[f.source] * c
+    for k, f in enumerate(factors):
+        if factor_inliers is not None:
+            w[index[f.pair]] += source_sizes[f.source] + 1.25 * float(factor_inliers[k])
+        else:
+            c = 1.0 + 1.25 * float(pair_cost[f.pair]) if pair_cost is not None and f.pair in pair_cost else 1.0
+            w[index[f.pair]] += source_sizes[f.source] * c
     if contiguous:
         cum = np.cumsum(w) - 0.5 * w  # midpoint rule: a pair goes to the chunk its centre of mass falls in
         total = float(w.sum()) or 1.0
