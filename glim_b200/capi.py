@@ -96,9 +96,7 @@ def lib():
     L.gb_find_neighbors.argtypes = [vp, sz, vp, i32, vp]
     L.gb_voxelgrid_sampling.argtypes = [vp, sz, vp, vp, vp, f64, vp, vp, vp, vp]
     for name in SYMBOLS:
-        fn = getattr(L, name)
-        if fn.restype is C.c_int and name not in ("gb_device_count",):
-            pass
+        getattr(L, name)  # AttributeError here means the library and include/glim_b200.h are out of sync
     _lib = L
     return L
 

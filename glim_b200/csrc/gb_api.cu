@@ -430,10 +430,8 @@ extern "C" gb_status gb_sweep_destroy(gb_sweep* s) { sweep_free(s); return GB_OK
 
 extern "C" gb_status gb_sweep_attach_slab(gb_sweep* s, void* device_slab_f32, size_t num_pairs) {
   GB_REQUIRE(s, "null sweep");
-  for (size_t f = 0; f < s->F && device_slab_f32; f++) {
-    // pair indices were baked into the descriptors at creation; validate the range on the host copy
-    (void)f;
-  }
+  for (size_t f = 0; f < s->F && device_slab_f32; f++)
+    GB_REQUIRE(s->h_pair[f] >= 0 && (size_t)s->h_pair[f] < num_pairs, "pair index out of range for this slab");
   s->d_slab = (float*)device_slab_f32;
   s->num_pairs = num_pairs;
   return GB_OK;

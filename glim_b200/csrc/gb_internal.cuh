@@ -67,7 +67,7 @@ struct gb_voxelmap {
   size_t bytes;
 };
 
-// device-side factor descriptor (64 B)
+// device-side factor descriptor (72 B)
 struct FactorDesc {
   const float4* p0;
   const float4* p1;
@@ -128,7 +128,7 @@ struct gb_sweep {
   size_t F;
   std::vector<gb_factor*> factors;
   FactorDesc* d_descs;
-  int2* d_tiles;          // {factor, begin}
+  int2* d_tiles;          // work items {factor, first point}, factor-major
   double* d_poses;        // F x 16 (T_lin)
   double* d_poses_eval;   // F x 16 (error mode)
   double* d_accum;        // F x acc_slots x GB_ACC_STRIDE, zero between sweeps (self-cleaning)

@@ -12,7 +12,10 @@ NonlinearFactorSetGPU::linearize:
                                                                    src/glim/mapping/global_mapping.cpp:234-283, :430-484
     livox_stress       odometry_gpu's factor rule on one 500 k-point MID-360-shaped frame
 
-Host-side logic only; every GPU operation goes through glim_b200.gpu (the C-ABI).
+This module (like glim_b200.synth) builds bench / test INPUTS; it is not part of the drop-in surface.  Host-side logic only;
+every GPU operation goes through glim_b200.gpu (the C-ABI).  When no context is given (CPU-only construction of the sample the
+reference arm times, CPU tests) the overlap GATE is evaluated by a host numpy twin of its definition -- that affects only which
+pairs the synthetic workload contains, never a product result.
 """
 from __future__ import annotations
 
