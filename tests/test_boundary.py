@@ -102,3 +102,39 @@ def test_slab_row_roundtrip():
     for k in ("H_tt", "H_ss", "H_ts", "b_t", "b_s"):
         assert np.allclose(back[k], rec[k], rtol=1e-6, atol=1e-6)
     assert back["error"] == 3.5 and back["num_inliers"] == 42.0
+
+
+def test_contiguous_partition_is_balanced_ordered_and_keeps_sources_together():
+    """The committed multi-GPU partition: contiguous chunks of the source-major factor order, equal cost, pairs whole; with
+    measured inlier counts the weights follow them."""
+    from glim_b200.workloads import Factor
+
+    rng = np.random.default_rng(3)
+    factors, pair = [], 0
+    for cur in range(1, 120):
+        for i in rng.choice(cur, size=min(cur, int(rng.integers(1, 9))), replace=False):
+            for l in (0, 1):
+                factors.append(Factor(int(i), l, cur, pair))
+            pair += 1
+    sizes = [50000] * 120
+    ov = {p: float(rng.uniform(0.2, 0.9)) for p in range(pair)}
+    for world in (2, 4, 8):
+        f_rank, p_rank = multi_gpu.shard_factors(factors, sizes, world, pair_cost=ov)
+        assert (np.diff(f_rank) >= 0).all() and set(f_rank) == set(range(world))  # contiguous, every rank has work
+        for f, r in zip(factors, f_rank):
+            assert r == p_rank[f.pair]
+        cost = np.array([sizes[f.source] * (1 + 1.25 * ov[f.pair]) for f in factors])
+        loads = np.array([cost[f_rank == r].sum() for r in range(world)])
+        assert loads.max() <= loads.mean() * 1.02 + cost.max() * 2
+        # a source cloud is split over at most two neighbouring ranks
+        by_src = {}
+        for f, r in zip(factors, f_rank):
+            by_src.setdefault(f.source, set()).add(int(r))
+        assert max(len(v) for v in by_src.values()) <= 2
+    inl = rng.uniform(0, 50000, size=len(factors))
+    f_rank, _ = multi_gpu.shard_factors(factors, sizes, 4, factor_inliers=inl)
+    cost = np.array([sizes[f.source] for f in factors]) + 1.25 * inl
+    loads = np.array([cost[f_rank == r].sum() for r in range(4)])
+    assert loads.max() <= loads.mean() * 1.02 + cost.max() * 2
+    lpt, _ = multi_gpu.shard_factors(factors, sizes, 4, pair_cost=ov, contiguous=False)
+    assert set(lpt) == {0, 1, 2, 3}
