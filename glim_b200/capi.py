@@ -24,6 +24,7 @@ SYMBOLS = [
     "gb_peer_slab_create", "gb_peer_slab_export", "gb_peer_slab_connect", "gb_peer_slab_destroy", "gb_sweep_attach_peer_slab",
     "gb_peer_slab_signal_wait", "gb_peer_slab_device_ptr", "gb_peer_slab_fetch", "gb_peer_slab_fetch_async",
     "gb_overlap", "gb_covariances", "gb_find_neighbors", "gb_voxelgrid_sampling",
+    "gb_deskew_pose_table", "gb_deskew",
 ]
 
 GB_SLAB_STRIDE = 96
@@ -95,6 +96,8 @@ def lib():
     L.gb_covariances.argtypes = [vp, sz, vp, vp, i32, i32, vp, vp]
     L.gb_find_neighbors.argtypes = [vp, sz, vp, i32, vp]
     L.gb_voxelgrid_sampling.argtypes = [vp, sz, vp, vp, vp, f64, vp, vp, vp, vp]
+    L.gb_deskew_pose_table.argtypes = [vp, vp, vp, sz, vp, vp, f64, sz, vp, vp, vp, vp]
+    L.gb_deskew.argtypes = [vp, vp, vp, vp, sz, vp, vp, f64, sz, vp, vp, vp, vp]
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError here means the library and include/glim_b200.h are out of sync
     _lib = L

@@ -125,3 +125,50 @@ class CloudPreprocessor:
         scan_end = stamp + (tms[-1] if len(tms) else 0.0)  # :174
         nb = find_neighbors(pts, p.k_correspondences, ctx)  # :182-183
         return PreprocessedFrame(stamp, scan_end, tms, ints, np.ascontiguousarray(pts), p.k_correspondences, nb)
+
+
+def _poses16(poses):
+    poses = np.asarray(poses, dtype=np.float64).reshape(-1, 4, 4)
+    return np.ascontiguousarray(np.swapaxes(poses, 1, 2)).reshape(-1, 16)
+
+
+def deskew_pose_table(T_imu_lidar, times, linear_vel=None, angular_vel=None, imu_times=None, imu_poses=None, stamp=0.0):
+    """Host half of CloudDeskewing::deskew: (time_indices (N,), table poses (M,4,4)).  Needs no GPU."""
+    from .capi import pose16
+
+    times = f64(times)
+    n = times.shape[0]
+    idx = np.empty((n,), np.int32)
+    table = np.empty((max(n, 1), 16))
+    m = C.c_size_t()
+    it = f64(imu_times) if imu_times is not None else None
+    ip = _poses16(imu_poses) if imu_poses is not None else None
+    lv = f64(linear_vel) if linear_vel is not None else None
+    av = f64(angular_vel) if angular_vel is not None else None
+    check(lib().gb_deskew_pose_table(ptr(pose16(T_imu_lidar)), ptr(lv), ptr(av), 0 if it is None else len(it), ptr(it), ptr(ip), float(stamp), n, ptr(times), ptr(idx), ptr(table), C.byref(m)))
+    return idx, np.swapaxes(table[: m.value].reshape(-1, 4, 4), 1, 2).copy()
+
+
+class CloudDeskewing:
+    """glim::CloudDeskewing (src/glim/common/cloud_deskewing.cpp): both overloads of deskew(), plus the optional fused second
+    transform of the call site (odometry_estimation_imu.cpp:313-316)."""
+
+    def __init__(self, ctx: Context | None = None):
+        self.ctx = ctx
+
+    def deskew(self, T_imu_lidar, times, points, linear_vel=None, angular_vel=None, imu_times=None, imu_poses=None, stamp=0.0, T_post=None):
+        from .capi import pose16
+
+        ctx = self.ctx or default_context()
+        times, points = f64(times), f64(points)
+        n = points.shape[0]
+        if n == 0:
+            return np.zeros((0, 4))
+        out = np.empty_like(points)
+        it = f64(imu_times) if imu_times is not None else None
+        ip = _poses16(imu_poses) if imu_poses is not None else None
+        lv = f64(linear_vel) if linear_vel is not None else None
+        av = f64(angular_vel) if angular_vel is not None else None
+        tp = pose16(T_post) if T_post is not None else None
+        check(lib().gb_deskew(ctx.h, ptr(pose16(T_imu_lidar)), ptr(lv), ptr(av), 0 if it is None else len(it), ptr(it), ptr(ip), float(stamp), n, ptr(times), ptr(points), ptr(tp), ptr(out)))
+        return out

@@ -181,6 +181,18 @@ GB_API gb_status gb_find_neighbors(gb_ctx* ctx, size_t n, const double* xyzw, in
  *      points / times / intensities, ascending packed-key order.  out arrays sized n; *num_out = count ---- */
 GB_API gb_status gb_voxelgrid_sampling(gb_ctx* ctx, size_t n, const double* xyzw, const double* times, const double* intensities, double resolution, double* out_xyzw, double* out_times, double* out_intensities, size_t* num_out);
 
+/* ---- glim::CloudDeskewing::deskew (src/glim/common/cloud_deskewing.cpp:11-55 constant velocity, :57-133 predicted IMU poses;
+ *      called at src/glim/odometry/odometry_estimation_imu.cpp:313).  n_imu > 0: imu_times / imu_poses (n_imu x 16, T_world_imu)
+ *      and `stamp` select the IMU-pose overload; n_imu == 0: linear_vel / angular_vel (either may be NULL = zero) select the
+ *      constant-velocity overload.  T_post (or NULL) is applied to every deskewed point as a second transform -- the
+ *      `pt = T_imu_lidar * pt` loop of odometry_estimation_imu.cpp:314-316 fused in.  Times must be ascending, as the
+ *      preprocessor leaves them (cloud_preprocessor.cpp:135-136).
+ *      gb_deskew_pose_table is the host half (time table + one pose per 0.1 ms slot); it needs no device. ---- */
+GB_API gb_status gb_deskew_pose_table(const double T_imu_lidar[16], const double* linear_vel, const double* angular_vel, size_t n_imu, const double* imu_times,
+                                      const double* imu_poses, double stamp, size_t n, const double* times, int32_t* time_indices /* n */, double* table_poses /* <= n x 16 */, size_t* table_size);
+GB_API gb_status gb_deskew(gb_ctx* ctx, const double T_imu_lidar[16], const double* linear_vel, const double* angular_vel, size_t n_imu, const double* imu_times, const double* imu_poses,
+                           double stamp, size_t n, const double* times, const double* xyzw, const double* T_post, double* out_xyzw);
+
 #ifdef __cplusplus
 }
 #endif

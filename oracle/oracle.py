@@ -63,6 +63,10 @@ def lib():
         L.go_knn_bruteforce.argtypes = [i32, vp, i32, i32, vp, vp]
         L.go_voxelgrid_sampling.restype = i32
         L.go_voxelgrid_sampling.argtypes = [i32, vp, vp, vp, f64, vp, vp, vp]
+        L.go_deskew_const_vel.restype = i32
+        L.go_deskew_const_vel.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
+        L.go_deskew_imu.restype = i32
+        L.go_deskew_imu.argtypes = [vp, i32, vp, vp, f64, i32, vp, vp, vp, vp]
         L.go_num_threads.restype = i32
         _lib = L
     return _lib
@@ -270,3 +274,22 @@ def voxelgrid_sampling(pts4, resolution, times=None, intensities=None):
     oi = np.empty((n,)) if it is not None else None
     m = lib().go_voxelgrid_sampling(n, _p(pts4), _p(t), _p(it), float(resolution), _p(op), _p(ot), _p(oi))
     return op[:m].copy(), (ot[:m].copy() if ot is not None else None), (oi[:m].copy() if oi is not None else None)
+
+
+def deskew_const_vel(T_imu_lidar, linear_vel, angular_vel, times, pts4, T_post=None):
+    """CloudDeskewing::deskew (constant velocity), src/glim/common/cloud_deskewing.cpp:11-55."""
+    pts4, times = _f64(pts4), _f64(times)
+    out = np.empty_like(pts4)
+    Tp = pose_colmajor(T_post) if T_post is not None else None
+    lib().go_deskew_const_vel(_p(pose_colmajor(T_imu_lidar)), _p(_f64(linear_vel)), _p(_f64(angular_vel)), pts4.shape[0], _p(times), _p(pts4), _p(Tp), _p(out))
+    return out
+
+
+def deskew_imu(T_imu_lidar, imu_times, imu_poses, stamp, times, pts4, T_post=None):
+    """CloudDeskewing::deskew (predicted IMU poses), src/glim/common/cloud_deskewing.cpp:57-133."""
+    pts4, times, imu_times = _f64(pts4), _f64(times), _f64(imu_times)
+    poses = np.ascontiguousarray(np.swapaxes(np.asarray(imu_poses, dtype=np.float64).reshape(-1, 4, 4), 1, 2)).reshape(-1, 16)
+    out = np.empty_like(pts4)
+    Tp = pose_colmajor(T_post) if T_post is not None else None
+    lib().go_deskew_imu(_p(pose_colmajor(T_imu_lidar)), len(imu_times), _p(imu_times), _p(poses), float(stamp), pts4.shape[0], _p(times), _p(pts4), _p(Tp), _p(out))
+    return out
