@@ -12,6 +12,7 @@
  *   - handles are created / destroyed by the caller with the matching _create / _destroy.
  *     A gb_factor BORROWS its cloud and voxel map (the C++ shim keeps shared_ptrs alive, as the
  *     reference factor does); destroying a cloud or map that a live factor uses is a caller bug.
+ *     Likewise a gb_sweep BORROWS its factors, and a sweep with a peer slab attached borrows the slab.
  *   - one gb_ctx per host thread / GPU (the reference drives each module from exactly one
  *     executor thread: src/glim/odometry/async_odometry_estimation.cpp:15).  A ctx owns one CUDA
  *     stream; all work of its handles is ordered on that stream.
