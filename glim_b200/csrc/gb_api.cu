@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <new>
 
 // ---------------------------------------------------------------------------------------------
@@ -75,7 +77,7 @@ static gb_status ctx_create(int device, cudaStream_t stream, bool own, gb_ctx** 
   c->num_sms = prop.multiProcessorCount;
   c->scratch = nullptr; c->scratch_cap = 0;
   c->pinned = nullptr; c->pinned_cap = 0;
-  c->launches = 0; c->epoch = 1; c->next_id = 1;
+  c->launches = 0;
   *out = c;
   return GB_OK;
 }
@@ -90,6 +92,8 @@ extern "C" gb_status gb_ctx_destroy(gb_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (gb_sweep* s : ctx->sweep_cache) sweep_free(s);
   ctx->sweep_cache.clear();
+  for (gb_pool_block& b : ctx->pool) { if (b.d) cudaFree(b.d); if (b.h) cudaFreeHost(b.h); }
+  ctx->pool.clear();
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -288,34 +292,79 @@ extern "C" gb_status gb_voxelmap_destroy(gb_voxelmap* m) {
 // ---------------------------------------------------------------------------------------------
 // factors and sweeps
 // ---------------------------------------------------------------------------------------------
+// Cross links factor <-> sweep (a factor may sit in cached sweeps of several contexts): guarded by one registry mutex.
+static std::mutex g_registry_mu;
+static std::atomic<uint64_t> g_next_factor_id{1};
+
 extern "C" gb_status gb_vgicp_factor_create(gb_ctx* ctx, const gb_voxelmap* target, const gb_cloud* source, int flags, gb_factor** out) {
   GB_REQUIRE(ctx && target && source && out, "null argument");
+  // clouds / voxel maps may have been uploaded through another context (another module thread): device memory is shared,
+  // and every producer call returns only after its stream has drained, so only the DEVICE has to match
   GB_REQUIRE(target->ctx->device == ctx->device && source->ctx->device == ctx->device, "cloud / voxel map live on another device");
   gb_factor* f = new (std::nothrow) gb_factor();
   if (!f) return GB_ERR_INTERNAL;
-  f->ctx = ctx; f->target = target; f->source = source; f->flags = flags; f->single = nullptr; f->id = ctx->next_id++;
+  f->ctx = ctx; f->target = target; f->source = source; f->flags = flags; f->single = nullptr; f->id = g_next_factor_id.fetch_add(1);
   *out = f;
   return GB_OK;
 }
 
+// return a retired sweep's blocks to its context's pool (the caller holds the context lock and has drained the stream)
+static void pool_put(gb_ctx* ctx, void* d, size_t d_cap, void* h, size_t h_cap) {
+  if (!d && !h) return;
+  if (ctx->pool.size() >= 64) {  // bounded: drop the smallest block
+    size_t k = 0;
+    for (size_t i = 1; i < ctx->pool.size(); i++) if (ctx->pool[i].d_cap < ctx->pool[k].d_cap) k = i;
+    if (ctx->pool[k].d) cudaFree(ctx->pool[k].d);
+    if (ctx->pool[k].h) cudaFreeHost(ctx->pool[k].h);
+    ctx->pool.erase(ctx->pool.begin() + k);
+  }
+  ctx->pool.push_back({d, d_cap, h, h_cap});
+}
+static bool pool_get(gb_ctx* ctx, size_t d_need, size_t h_need, gb_pool_block* out) {
+  int best = -1;
+  for (size_t i = 0; i < ctx->pool.size(); i++) {
+    const gb_pool_block& b = ctx->pool[i];
+    if (b.d_cap >= d_need && b.h_cap >= h_need && b.d_cap <= 4 * d_need + (1 << 16) && (best < 0 || b.d_cap < ctx->pool[best].d_cap)) best = (int)i;
+  }
+  if (best < 0) return false;
+  *out = ctx->pool[best];
+  ctx->pool.erase(ctx->pool.begin() + best);
+  return true;
+}
+
 static void sweep_free(gb_sweep* s) {
   if (!s) return;
-  cudaSetDevice(s->ctx->device);
-  cudaStreamSynchronize(s->ctx->stream);
-  if (s->d_descs) cudaFree(s->d_descs);
+  gb_ctx* ctx = s->ctx;
+  GB_LOCK(ctx);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  {
+    std::lock_guard<std::mutex> reg(g_registry_mu);
+    for (gb_factor* f : s->factors) {
+      if (!f) continue;  // already destroyed (the sweep is stale)
+      auto it = std::find(f->users.begin(), f->users.end(), s);
+      if (it != f->users.end()) f->users.erase(it);
+    }
+  }
+  for (int k = 0; k < 2; k++) if (s->pose_ev[k]) cudaEventDestroy(s->pose_ev[k]);
   if (s->d_pair_ptr) cudaFree(s->d_pair_ptr);
-  if (s->h_poses) cudaFreeHost(s->h_poses);
+  pool_put(ctx, s->pool_d, s->pool_d_cap, s->pool_h, s->pool_h_cap);
   delete s;
 }
 
 extern "C" gb_status gb_vgicp_factor_destroy(gb_factor* f) {
   if (!f) return GB_OK;
-  gb_ctx* ctx = f->ctx;
-  if (f->single) sweep_free(f->single);
-  // cached sweeps that reference this factor are stale from now on
-  ctx->epoch++;
-  for (gb_sweep* s : ctx->sweep_cache) sweep_free(s);
-  ctx->sweep_cache.clear();
+  if (f->single) { sweep_free(f->single); f->single = nullptr; }
+  // sweeps that reference this factor (cached ones of any context, or caller-owned ones) are stale from now on; they are
+  // freed by their owners (lazily for cached sweeps).  Only THOSE sweeps: a frame's other factor sets stay cached.
+  {
+    std::lock_guard<std::mutex> reg(g_registry_mu);
+    for (gb_sweep* s : f->users) {
+      s->stale = true;
+      for (auto& p : s->factors) if (p == f) p = nullptr;
+    }
+    f->users.clear();
+  }
   delete f;
   return GB_OK;
 }
@@ -329,36 +378,42 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   GB_REQUIRE(ctx && out, "null argument");
   GB_REQUIRE(F == 0 || factors, "null factor list");
   *out = nullptr;
+  // validate before anything is allocated
+  uint64_t total_pts = 0;
+  for (size_t f = 0; f < F; f++) {
+    GB_REQUIRE(factors[f], "null factor");
+    GB_REQUIRE(factors[f]->source->ctx->device == ctx->device && factors[f]->target->ctx->device == ctx->device, "factor lives on another device");
+    total_pts += factors[f]->source->n;
+  }
+  GB_LOCK(ctx);
   GB_CUDA(cudaSetDevice(ctx->device));
   gb_sweep* s = new (std::nothrow) gb_sweep();
   if (!s) return GB_ERR_INTERNAL;
   s->ctx = ctx; s->F = F; s->factors.assign(factors, factors + F);
   s->d_descs = nullptr; s->d_tiles = nullptr; s->d_poses = nullptr; s->d_poses_eval = nullptr; s->d_accum = nullptr; s->d_done = nullptr; s->d_out = nullptr;
-  s->h_poses = nullptr; s->h_poses_eval = nullptr; s->h_out = nullptr; s->d_slab = nullptr; s->num_pairs = 0;
+  s->h_poses_eval = nullptr; s->h_out = nullptr; s->d_slab = nullptr; s->num_pairs = 0;
   s->d_tile_ctr = nullptr; s->ctr_base = 0;
   s->peer = nullptr; s->d_pair_ptr = nullptr; s->d_pair_factors = nullptr; s->d_pair_done = nullptr; s->d_peer_tables = nullptr;
-  s->num_tiles = 0; s->point_factors = 0; s->algorithmic_bytes = 0; s->key = 0; s->epoch = ctx->epoch;
+  s->num_tiles = 0; s->point_factors = 0; s->algorithmic_bytes = 0; s->key = 0; s->stale = false;
+  s->h_pose_slot[0] = s->h_pose_slot[1] = nullptr; s->pose_ev[0] = s->pose_ev[1] = nullptr; s->pose_slot = 0;
+  s->pool_d = nullptr; s->pool_d_cap = 0; s->pool_h = nullptr; s->pool_h_cap = 0;
 
-  // tile size: enough tiles to balance the persistent grid, large enough to amortise the per-tile reduction
-  uint64_t total_pts = 0;
-  for (size_t f = 0; f < F; f++) {
-    GB_REQUIRE(factors[f] && factors[f]->ctx == ctx, "factor belongs to another context");
-    total_pts += factors[f]->source->n;
-  }
-  s->min_blocks = std::min(4, std::max(2, env_int("GB_MIN_BLOCKS", 2)));
-  s->static_first = env_int("GB_STATIC_FIRST", 1);
-  const int ctas_per_sm = env_int("GB_CTAS_PER_SM", s->min_blocks);
+  // kernel generation and work-item size
+  s->kernel_version = env_int("GB_KERNEL", 4) == 3 ? 3 : 4;
+  s->stage_points = env_int("GB_STAGE", 128) == 64 ? 64 : 128;
+  const int T = s->kernel_version == 4 ? s->stage_points : 32;
+  const int ctas_per_sm = (s->kernel_version == 4 && s->stage_points == 64) ? 3 : 2;
   const int capacity = ctx->num_sms * ctas_per_sm;
   int tile = env_int("GB_TILE", 0);
   if (tile <= 0) {
-    // work items are per WARP: ~6 items per warp drawn dynamically, between 128 and 2048 points each (measured optimum on
-    // B200 across the BASELINE workloads, profiles/tune_sweep_r01.txt; for small sweeps both more-and-smaller and
-    // fewer-and-larger items were measured slower than 128-point items)
+    // work items are per WARP: ~GB_ITEMS_PER_WARP items per warp (first one static, the rest drawn dynamically), between
+    // one stage and 2048 points each (profiles/tune_sweep_r0*.txt)
     const uint64_t warps = (uint64_t)capacity * 8;
-    const uint64_t want = total_pts / (warps * 6) + 1;
-    tile = (int)std::min<uint64_t>(2048, std::max<uint64_t>(128, (want + 31) / 32 * 32));
+    const uint64_t ipw = (uint64_t)std::max(1, env_int("GB_ITEMS_PER_WARP", s->kernel_version == 4 ? 4 : 6));
+    const uint64_t want = total_pts / (warps * ipw) + 1;
+    tile = (int)std::min<uint64_t>(2048, std::max<uint64_t>(s->kernel_version == 4 ? T : 128, want));
   }
-  tile = std::min(1 << 20, std::max(32, (tile + 31) / 32 * 32));
+  tile = std::min(1 << 20, std::max(T, (tile + T - 1) / T * T));
   s->tile_size = tile;
 
   std::vector<FactorDesc> descs(F);
@@ -381,28 +436,37 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     D.num_tiles = nt;
     for (int t = 0; t < nt; t++) tiles.push_back(make_int2((int)f, t * tile));
     s->point_factors += (uint64_t)D.n;
-    // B_f of SURVEY 8(d): 48 B per source point (+12 with normals), 48 B per target voxel, 16 B per bucket, pose in + record out
+    // B_f of SURVEY 8(d): 48 B per source point, 48 B per target voxel, 16 B per bucket, pose in + record out.
     // The bucket term is charged at the SMALLEST table that could hold the voxels (16384 doubled until >= V), not at
     // our deliberately sparse table (>= 8 V): padding we added for speed must not inflate the achieved-GB/s figure.
     uint64_t nb_ref = 16384;
     while (nb_ref < (uint64_t)fa->target->num_voxels) nb_ref *= 2;
-    s->algorithmic_bytes += (uint64_t)D.n * (48 + ((fa->flags & GB_FACTOR_SURFACE_VALIDATION) ? 12 : 0)) + (uint64_t)fa->target->num_voxels * 48 + nb_ref * 16 + 64 + 488;
+    s->algorithmic_bytes += (uint64_t)D.n * 48 + (uint64_t)fa->target->num_voxels * 48 + nb_ref * 16 + 64 + 488;
   }
   s->num_tiles = (int)tiles.size();
   s->grid = std::max(1, std::min((s->num_tiles + 7) / 8, capacity));
   // ~64 items per accumulator copy: sweeps with few factors (an odometry frame, a single pair) would otherwise
-  // serialise hundreds of fp64 atomics on the same addresses
+  // serialise hundreds of fp64 reductions on the same addresses
   s->acc_slots = 1;
   while (F > 0 && s->acc_slots < 16 && (uint64_t)s->num_tiles > (uint64_t)F * 64 * s->acc_slots) s->acc_slots *= 2;
 
   if (F > 0) {
-    // one device allocation, one pinned allocation
+    // one device block, one pinned block -- taken from the context's pool when a retired sweep left a fitting one
     const size_t b_desc = align_up(sizeof(FactorDesc) * F, 256), b_tiles = align_up(sizeof(int2) * tiles.size(), 256), b_pose = align_up(sizeof(double) * 16 * F, 256);
     const size_t b_acc = align_up(sizeof(double) * GB_ACC_STRIDE * F * s->acc_slots, 256), b_done = align_up(sizeof(unsigned) * F + 16, 256), b_out = align_up(sizeof(double) * GB_OUT_DOUBLES * F, 256);
     const size_t total = b_desc + b_tiles + 2 * b_pose + b_acc + b_done + b_out;
-    char* d = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d, total);
-    if (e != cudaSuccess) { delete s; gb_set_error("cudaMalloc(%zu): %s", total, cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
+    const size_t h_total = 3 * b_pose + b_out + align_up(sizeof(FactorDesc) * F, 256) + b_tiles;
+    gb_pool_block blk{nullptr, 0, nullptr, 0};
+    if (!pool_get(ctx, total, h_total, &blk)) {
+      cudaError_t e = cudaMalloc(&blk.d, total);
+      if (e != cudaSuccess) { delete s; gb_set_error("cudaMalloc(%zu): %s", total, cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
+      blk.d_cap = total;
+      e = cudaMallocHost(&blk.h, h_total);
+      if (e != cudaSuccess) { cudaFree(blk.d); delete s; gb_set_error("cudaMallocHost: %s", cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
+      blk.h_cap = h_total;
+    }
+    s->pool_d = blk.d; s->pool_d_cap = blk.d_cap; s->pool_h = blk.h; s->pool_h_cap = blk.h_cap;
+    char* d = (char*)blk.d;
     s->d_descs = (FactorDesc*)d; d += b_desc;
     s->d_tiles = (int2*)d; d += b_tiles;
     s->d_poses = (double*)d; d += b_pose;
@@ -412,16 +476,23 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     s->d_tile_ctr = (unsigned long long*)(d + align_up(sizeof(unsigned) * F, 8));
     d += b_done;
     s->d_out = (double*)d;
-    char* h = nullptr;
-    e = cudaMallocHost((void**)&h, 2 * b_pose + b_out);
-    if (e != cudaSuccess) { cudaFree(s->d_descs); delete s; gb_set_error("cudaMallocHost: %s", cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
-    s->h_poses = (double*)h; s->h_poses_eval = (double*)(h + b_pose); s->h_out = (double*)(h + 2 * b_pose);
+    char* h = (char*)blk.h;
+    s->h_pose_slot[0] = (double*)h; s->h_pose_slot[1] = (double*)(h + b_pose); s->h_poses_eval = (double*)(h + 2 * b_pose); s->h_out = (double*)(h + 3 * b_pose);
+    char* h_desc = h + 3 * b_pose + b_out;
+    char* h_tiles = h_desc + align_up(sizeof(FactorDesc) * F, 256);
+    memcpy(h_desc, descs.data(), sizeof(FactorDesc) * F);
+    memcpy(h_tiles, tiles.data(), sizeof(int2) * tiles.size());
     cudaStream_t st = ctx->stream;
-    e = cudaMemcpyAsync(s->d_descs, descs.data(), sizeof(FactorDesc) * F, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(s->d_descs, h_desc, sizeof(FactorDesc) * F, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_tiles, h_tiles, sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_accum, 0, b_acc + b_done, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // descs / tiles are stack-local vectors
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&s->pose_ev[k], cudaEventDisableTiming);
     if (e != cudaSuccess) { sweep_free(s); gb_set_error("sweep setup: %s", cudaGetErrorString(e)); return GB_ERR_CUDA; }
+    // no synchronisation: the staging lives in the sweep's own pinned block, and everything that follows is stream ordered
+  }
+  {
+    std::lock_guard<std::mutex> reg(g_registry_mu);
+    for (gb_factor* f : s->factors) f->users.push_back(s);
   }
   *out = s;
   return GB_OK;
@@ -440,26 +511,37 @@ extern "C" gb_status gb_sweep_attach_slab(gb_sweep* s, void* device_slab_f32, si
 extern "C" gb_status gb_sweep_set_poses(gb_sweep* s, const double* T) {
   GB_REQUIRE(s && (s->F == 0 || T), "null argument");
   if (s->F == 0) return GB_OK;
-  // the previous H2D from this pinned buffer must have been consumed
-  GB_CUDA(cudaStreamSynchronize(s->ctx->stream));
-  memcpy(s->h_poses, T, sizeof(double) * 16 * s->F);
-  GB_CUDA(cudaMemcpyAsync(s->d_poses, s->h_poses, sizeof(double) * 16 * s->F, cudaMemcpyHostToDevice, s->ctx->stream));
+  GB_LOCK(s->ctx);
+  // double-buffered pinned staging: wait only for the H2D that read THIS slot two calls ago (normally long finished)
+  const int k = s->pose_slot;
+  s->pose_slot ^= 1;
+  GB_CUDA(cudaEventSynchronize(s->pose_ev[k]));
+  memcpy(s->h_pose_slot[k], T, sizeof(double) * 16 * s->F);
+  GB_CUDA(cudaMemcpyAsync(s->d_poses, s->h_pose_slot[k], sizeof(double) * 16 * s->F, cudaMemcpyHostToDevice, s->ctx->stream));
+  GB_CUDA(cudaEventRecord(s->pose_ev[k], s->ctx->stream));
   return GB_OK;
 }
 static gb_status sweep_set_eval_poses(gb_sweep* s, const double* T) {
   if (s->F == 0) return GB_OK;
+  // the eval poses are only used by the blocking error calls (each ends with a stream sync): single buffer is safe
   memcpy(s->h_poses_eval, T, sizeof(double) * 16 * s->F);
   GB_CUDA(cudaMemcpyAsync(s->d_poses_eval, s->h_poses_eval, sizeof(double) * 16 * s->F, cudaMemcpyHostToDevice, s->ctx->stream));
   return GB_OK;
 }
+static gb_status sweep_launch(gb_sweep* s, int mode) {
+  if (s->stale) { gb_set_error("a factor of this sweep has been destroyed"); return GB_ERR_INVALID_ARGUMENT; }
+  GB_CUDA(cudaSetDevice(s->ctx->device));
+  return gb_launch_sweep(s, mode);
+}
 extern "C" gb_status gb_sweep_launch(gb_sweep* s) {
   GB_REQUIRE(s, "null sweep");
-  GB_CUDA(cudaSetDevice(s->ctx->device));
-  return gb_launch_sweep(s, GB_MODE_LINEARIZE);
+  GB_LOCK(s->ctx);
+  return sweep_launch(s, GB_MODE_LINEARIZE);
 }
 extern "C" gb_status gb_sweep_fetch(gb_sweep* s, gb_linearized6* out) {
   GB_REQUIRE(s && (s->F == 0 || out), "null argument");
   if (s->F == 0) return GB_OK;
+  GB_LOCK(s->ctx);
   static_assert(sizeof(gb_linearized6) == sizeof(double) * GB_OUT_DOUBLES, "gb_linearized6 layout");
   GB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, sizeof(double) * GB_OUT_DOUBLES * s->F, cudaMemcpyDeviceToHost, s->ctx->stream));
   GB_CUDA(cudaStreamSynchronize(s->ctx->stream));
@@ -488,8 +570,12 @@ static gb_status cached_sweep(gb_ctx* ctx, size_t F, gb_factor* const* factors, 
     key = (key ^ factors[f]->id) * 1099511628211ull;
   }
   key ^= (uint64_t)F << 48;
+  // drop the sweeps whose factors died since (only those)
+  for (size_t i = 0; i < ctx->sweep_cache.size();) {
+    if (ctx->sweep_cache[i]->stale) { sweep_free(ctx->sweep_cache[i]); ctx->sweep_cache.erase(ctx->sweep_cache.begin() + i); } else i++;
+  }
   for (gb_sweep* s : ctx->sweep_cache)
-    if (s->key == key && s->F == F && s->epoch == ctx->epoch && std::equal(s->factors.begin(), s->factors.end(), factors)) { *out = s; return GB_OK; }
+    if (s->key == key && s->F == F && std::equal(s->factors.begin(), s->factors.end(), factors)) { *out = s; return GB_OK; }
   gb_sweep* s = nullptr;
   GB_CHECK(gb_sweep_create(ctx, F, factors, nullptr, &s));
   s->key = key;
@@ -503,10 +589,11 @@ extern "C" gb_status gb_factor_set_linearize(gb_ctx* ctx, size_t F, gb_factor* c
   GB_REQUIRE(ctx, "null ctx");
   if (F == 0) return GB_OK;
   GB_REQUIRE(factors && T && out, "null argument");
+  GB_LOCK(ctx);
   gb_sweep* s = nullptr;
   GB_CHECK(cached_sweep(ctx, F, factors, &s));
   GB_CHECK(gb_sweep_set_poses(s, T));
-  GB_CHECK(gb_launch_sweep(s, GB_MODE_LINEARIZE));
+  GB_CHECK(sweep_launch(s, GB_MODE_LINEARIZE));
   return gb_sweep_fetch(s, out);
 }
 
@@ -514,11 +601,12 @@ extern "C" gb_status gb_factor_set_error(gb_ctx* ctx, size_t F, gb_factor* const
   GB_REQUIRE(ctx, "null ctx");
   if (F == 0) return GB_OK;
   GB_REQUIRE(factors && T_lin && T_eval && errors, "null argument");
+  GB_LOCK(ctx);
   gb_sweep* s = nullptr;
   GB_CHECK(cached_sweep(ctx, F, factors, &s));
   GB_CHECK(gb_sweep_set_poses(s, T_lin));
   GB_CHECK(sweep_set_eval_poses(s, T_eval));
-  GB_CHECK(gb_launch_sweep(s, GB_MODE_ERROR));
+  GB_CHECK(sweep_launch(s, GB_MODE_ERROR));
   GB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, sizeof(double) * GB_OUT_DOUBLES * F, cudaMemcpyDeviceToHost, ctx->stream));
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
   for (size_t f = 0; f < F; f++) errors[f] = s->h_out[f * GB_OUT_DOUBLES + 120];
@@ -532,19 +620,21 @@ static gb_status single_sweep(gb_factor* f, gb_sweep** out) {
 }
 extern "C" gb_status gb_vgicp_linearize(gb_factor* f, const double T[16], gb_linearized6* out) {
   GB_REQUIRE(f && T && out, "null argument");
+  GB_LOCK(f->ctx);
   gb_sweep* s = nullptr;
   GB_CHECK(single_sweep(f, &s));
   GB_CHECK(gb_sweep_set_poses(s, T));
-  GB_CHECK(gb_launch_sweep(s, GB_MODE_LINEARIZE));
+  GB_CHECK(sweep_launch(s, GB_MODE_LINEARIZE));
   return gb_sweep_fetch(s, out);
 }
 extern "C" gb_status gb_vgicp_error(gb_factor* f, const double T_lin[16], const double T_eval[16], double* error) {
   GB_REQUIRE(f && T_lin && T_eval && error, "null argument");
+  GB_LOCK(f->ctx);
   gb_sweep* s = nullptr;
   GB_CHECK(single_sweep(f, &s));
   GB_CHECK(gb_sweep_set_poses(s, T_lin));
   GB_CHECK(sweep_set_eval_poses(s, T_eval));
-  GB_CHECK(gb_launch_sweep(s, GB_MODE_ERROR));
+  GB_CHECK(sweep_launch(s, GB_MODE_ERROR));
   GB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, sizeof(double) * GB_OUT_DOUBLES, cudaMemcpyDeviceToHost, f->ctx->stream));
   GB_CUDA(cudaStreamSynchronize(f->ctx->stream));
   *error = s->h_out[120];

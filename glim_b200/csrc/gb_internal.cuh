@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -91,7 +92,8 @@ struct gb_factor {
   const gb_cloud* source;
   int flags;
   gb_sweep* single;  // lazily created 1-factor sweep
-  uint64_t id;
+  uint64_t id;       // process-wide unique
+  std::vector<gb_sweep*> users;  // sweeps (of any context) that reference this factor; guarded by the registry mutex
 };
 
 #define GB_MAX_PEERS 8
@@ -137,7 +139,6 @@ struct gb_sweep {
   unsigned long long* d_tile_ctr;  // dynamic tile queue head, monotonic across launches
   unsigned long long ctr_base;     // value of the counter at the start of the next launch
   double* d_out;          // F x 122
-  double* h_poses;        // pinned
   double* h_poses_eval;   // pinned
   double* h_out;          // pinned
   float* d_slab;
@@ -149,12 +150,19 @@ struct gb_sweep {
   PeerPush* d_peer_tables;        // [2]: one per step parity
   std::vector<int> h_pair;        // pair id per factor
   int num_tiles, tile_size, grid;   // work items, points per item, CTAs
-  int min_blocks;                   // kernel register-budget variant (CTAs per SM)
-  int static_first;                 // first item of a warp = its index (1) or drawn from the queue (0)
+  int kernel_version;               // 4 = bulk-async staged kernel (default), 3 = round-1 kernel (GB_KERNEL=3)
+  int stage_points;                 // v4: points per shared-memory stage (128: 2 CTAs / SM; 64: 3 CTAs / SM)
   uint64_t point_factors, algorithmic_bytes;
   uint64_t key;           // cache key
-  uint64_t epoch;
+  bool stale;             // a factor of this sweep was destroyed: it can no longer be launched
+  double* h_pose_slot[2]; // pinned pose staging, double buffered (no stream sync in gb_sweep_set_poses)
+  cudaEvent_t pose_ev[2]; // recorded after the H2D that read the slot
+  int pose_slot;
+  void* pool_d; size_t pool_d_cap;  // the blocks this sweep took from its context's pool
+  void* pool_h; size_t pool_h_cap;
 };
+
+struct gb_pool_block { void* d; size_t d_cap; void* h; size_t h_cap; };
 
 struct gb_ctx {
   int device;
@@ -166,10 +174,13 @@ struct gb_ctx {
   void* pinned;
   size_t pinned_cap;
   uint64_t launches;
-  uint64_t epoch;          // bumped whenever a factor dies -> cached sweeps are stale
-  uint64_t next_id;
   std::vector<gb_sweep*> sweep_cache;
+  std::vector<gb_pool_block> pool;  // device + pinned blocks of retired sweeps, reused by the next gb_sweep_create
+  // A context may be driven from more than one host thread (a frame cloned by the odometry thread is later used by the
+  // sub-mapping thread): every entry point that touches the stream, the scratch arena or the caches takes this lock.
+  std::recursive_mutex mu;
 };
+#define GB_LOCK(ctx) std::lock_guard<std::recursive_mutex> gb_lock__((ctx)->mu)
 
 gb_status gb_ctx_scratch(gb_ctx* ctx, size_t bytes, void** out);  // device scratch, valid until the next call
 gb_status gb_ctx_pinned(gb_ctx* ctx, size_t bytes, void** out);   // pinned host staging, same lifetime rule
@@ -177,6 +188,7 @@ gb_status gb_ctx_pinned(gb_ctx* ctx, size_t bytes, void** out);   // pinned host
 // kernel launchers (gb_kernels_*.cu)
 enum { GB_MODE_LINEARIZE = 0, GB_MODE_ERROR = 1 };
 gb_status gb_launch_sweep(gb_sweep* s, int mode);
+size_t gb_sweep4_smem_bytes(int stage_points);
 gb_status gb_launch_peer_signal_wait(gb_peer_slab* ps);
 gb_status gb_launch_overlap(gb_ctx* ctx, int num_targets, const FactorDesc* d_descs, const double* d_poses, int n, int* d_count);
 gb_status gb_cloud_reorder_impl(gb_ctx* ctx, gb_cloud* c, const void* staged /* device copy of the planes in original order */, size_t b0, size_t b1, size_t b2, size_t b3);

@@ -7,20 +7,29 @@
 // oracle: go_vgicp_linearize_gpumap / go_vgicp_error_gpumap / go_overlap_gpumap (oracle/glim_oracle.c).
 //
 // One launch covers a whole factor set.  Work unit = an item of up to `chunk` consecutive source
-// points of one factor; items are laid out factor-major and drawn from a global queue by the warps of
-// a persistent grid, so at any instant the grid works on a window of a few consecutive factors whose
-// source cloud and voxel table stay L2 resident.  Per inlier (one lane):
+// points of one factor; items are laid out factor-major and processed by the warps of a persistent grid
+// (first item = warp index, further items from a global queue), so at any instant the grid works on a
+// window of a few consecutive factors whose source cloud and voxel tables stay L2 resident.
+// Per inlier (one lane):
 //   q = R a + t -> voxel coord -> hash probe (16-byte buckets) -> 48-byte voxel record ->
 //   S = C_B + R C_A R^T, M = S^-1 (symmetric 3x3) -> accumulate the 21 unique entries of
 //   H_tt = J_t^T M J_t (J_t = [-hat(q) | I]), the 6 of b_t = J_t^T M r, the error r^T M r and the
 //   inlier count: 29 registers.
-// Per item: transposing warp reduce-scatter (31 shuffles for 32 values) and 29 fp64 atomics into the
+// Per item: transposing warp reduce-scatter (31 shuffles for 32 values) and 29 fp64 reductions (RED) into the
 // factor's accumulator.  The warp that retires a factor's last item runs the fp64 epilogue:
 // H_ts = -H_tt Ad, H_ss = Ad^T H_tt Ad, b_s = -Ad^T b_t with Ad = AdjointMap(delta),
-// writes the 122-double record (and adds it to the pair slab when one is attached), and re-zeroes
-// the accumulator for the next sweep.
+// writes the 122-double record (and pushes the finished pair row to every rank's slab when one is attached),
+// and re-zeroes the accumulator for the next sweep.
+//
+// Two generations of the sweep kernel live here:
+//   k_vgicp_sweep4  (default)  source tiles staged into shared memory by 1-D bulk async copies (cp.async.bulk /
+//                   UBLKCP + mbarrier), double-buffered per warp; descriptor / pose cache in shared memory for small
+//                   factor sets; release-atomic tickets published lazily (no __threadfence, no L1 flush per item);
+//                   carry-over hit queue so the derivative pass always runs on full warps.
+//   k_vgicp_sweep3  (GB_KERNEL=3) the round-1 kernel: register-staged loads, fence + ticket per item.  Kept for A/B.
 #include "gb_internal.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -41,6 +50,15 @@ __device__ __forceinline__ PoseF load_pose(const float* s) {
   return P;
 }
 
+// pose -> fp32 row-major R | t  (Isometry3f cast of the reference GPU factor)
+__device__ __forceinline__ PoseF pose_from_colmajor(const double* __restrict__ T) {
+  PoseF P;
+  P.r00 = (float)T[0]; P.r01 = (float)T[4]; P.r02 = (float)T[8];  P.tx = (float)T[12];
+  P.r10 = (float)T[1]; P.r11 = (float)T[5]; P.r12 = (float)T[9];  P.ty = (float)T[13];
+  P.r20 = (float)T[2]; P.r21 = (float)T[6]; P.r22 = (float)T[10]; P.tz = (float)T[14];
+  return P;
+}
+
 // q = R a + t with the canonical FMA order (bit-exact with transform_f32 in the oracle)
 __device__ __forceinline__ void transform(const PoseF& P, float ax, float ay, float az, float& qx, float& qy, float& qz) {
   qx = fmaf(P.r00, ax, fmaf(P.r01, ay, fmaf(P.r02, az, P.tx)));
@@ -48,8 +66,9 @@ __device__ __forceinline__ void transform(const PoseF& P, float ax, float ay, fl
   qz = fmaf(P.r20, ax, fmaf(P.r21, ay, fmaf(P.r22, az, P.tz)));
 }
 
-// M = (C_B + R C_A R^T)^-1, symmetric 3x3 (xx xy xz yy yz zz)
-__device__ __forceinline__ void fused_mahalanobis(
+// M = (C_B + R C_A R^T)^-1, symmetric 3x3 (xx xy xz yy yz zz).  Returns false when the fused covariance is singular or
+// non-finite: such a point contributes nothing and is not counted (oracle: mat3_inv fails -> point skipped).
+__device__ __forceinline__ bool fused_mahalanobis(
   const PoseF& P, float cxx, float cxy, float cxz, float cyy, float cyz, float czz,  // C_A
   float bxx, float bxy, float bxz, float byy, float byz, float bzz,                  // C_B
   float& mxx, float& mxy, float& mxz, float& myy, float& myz, float& mzz) {
@@ -80,6 +99,67 @@ __device__ __forceinline__ void fused_mahalanobis(
   const float det = sxx * c00 + sxy * c01 + sxz * c02;
   const float id = __fdividef(1.0f, det);
   mxx = c00 * id; mxy = c01 * id; mxz = c02 * id; myy = c11 * id; myz = c12 * id; mzz = c22 * id;
+  return det != 0.0f && fabsf(det) <= 3.0e38f;
+}
+
+// One inlier's contribution: source point (a0 = {x y z c00}, a1 = {c01 c02 c11 c12}, a2 = c22), target voxel record
+// (v0 = {mx my mz c00}, v1 = {c01 c02 c11 c12}, v2.x = c22), evaluated at pose Pe.  acc[0..20] = upper triangle of H_tt
+// (row-major), acc[21..26] = b_t, acc[27] = error, acc[28] = inlier count.
+template <int MODE>
+__device__ __forceinline__ void accumulate_hit(float (&acc)[32], const PoseF& Pe, const float4 a0, const float4 a1, const float a2, const float4 v0, const float4 v1, const float4 v2) {
+  float qx, qy, qz;
+  transform(Pe, a0.x, a0.y, a0.z, qx, qy, qz);
+  float mxx, mxy, mxz, myy, myz, mzz;
+  if (!fused_mahalanobis(Pe, a0.w, a1.x, a1.y, a1.z, a1.w, a2, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, mxx, mxy, mxz, myy, myz, mzz)) return;
+  const float rx = v0.x - qx, ry = v0.y - qy, rz = v0.z - qz;
+  const float wx = mxx * rx + mxy * ry + mxz * rz;
+  const float wy = mxy * rx + myy * ry + myz * rz;
+  const float wz = mxz * rx + myz * ry + mzz * rz;
+  acc[27] += rx * wx + ry * wy + rz * wz;
+  acc[28] += 1.0f;
+  if (MODE == GB_MODE_LINEARIZE) {
+    // G = hat(q) M   (rows: rotation, cols: translation block of H_tt)
+    const float g00 = qy * mxz - qz * mxy, g01 = qy * myz - qz * myy, g02 = qy * mzz - qz * myz;
+    const float g10 = qz * mxx - qx * mxz, g11 = qz * mxy - qx * myz, g12 = qz * mxz - qx * mzz;
+    const float g20 = qx * mxy - qy * mxx, g21 = qx * myy - qy * mxy, g22 = qx * myz - qy * mxz;
+    // H_rr = G hat(q)^T : row i = q x g_i   (upper triangle)
+    acc[0] += qy * g02 - qz * g01;
+    acc[1] += qz * g00 - qx * g02;
+    acc[2] += qx * g01 - qy * g00;
+    acc[3] += g00; acc[4] += g01; acc[5] += g02;
+    acc[6] += qz * g10 - qx * g12;
+    acc[7] += qx * g11 - qy * g10;
+    acc[8] += g10; acc[9] += g11; acc[10] += g12;
+    acc[11] += qx * g21 - qy * g20;
+    acc[12] += g20; acc[13] += g21; acc[14] += g22;
+    acc[15] += mxx; acc[16] += mxy; acc[17] += mxz; acc[18] += myy; acc[19] += myz; acc[20] += mzz;
+    // b_t = [q x w ; w]
+    acc[21] += qy * wz - qz * wy;
+    acc[22] += qz * wx - qx * wz;
+    acc[23] += qx * wy - qy * wx;
+    acc[24] += wx; acc[25] += wy; acc[26] += wz;
+  }
+}
+
+// probe result of one point given its first two buckets (b, b1 fetched together: adjacent 16-byte slots, one round trip)
+__device__ __forceinline__ int resolve_probe(const FactorDesc& D, const int4 b, const int4 b1, uint32_t h, int cx, int cy, int cz) {
+  int v = -1;
+  if (b.w >= 0) {
+    if (b.x == cx && b.y == cy && b.z == cz) {
+      v = b.w;
+    } else if (D.max_scan > 1 && b1.w >= 0) {
+      if (b1.x == cx && b1.y == cy && b1.z == cz) {
+        v = b1.w;
+      } else {
+        for (int k = 2; k < D.max_scan; k++) {  // rare: longer collision chain
+          const int4 bb = __ldg(&D.buckets[(h + (uint32_t)k) & D.mask]);
+          if (bb.w < 0) break;
+          if (bb.x == cx && bb.y == cy && bb.z == cz) { v = bb.w; break; }
+        }
+      }
+    }
+  }
+  return v;
 }
 
 // Transposing warp reduction: on return lane l holds sum over the warp of v[l] (in v[0]).
@@ -97,7 +177,6 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane)
   return v[0];
 }
 
-// fp64 epilogue of one factor, executed by warp 0 of the CTA that retired the factor's last tile.
 // slab row element e (see GB_SLAB_STRIDE in include/glim_b200.h) -> index in the 122-double record
 __device__ __forceinline__ int slab_to_record(int e) {
   if (e < 21 || (e >= 57 && e < 78)) {  // upper triangles of H_tt / H_ss, row-major (i <= j)
@@ -112,24 +191,32 @@ __device__ __forceinline__ int slab_to_record(int e) {
   return 120 + (e - 90);              // error, num_inliers
 }
 
+// release / acquire building blocks of the per-factor and per-pair tickets.  atom.release = MEMBAR.ALL.GPU + ATOMG: it does
+// NOT invalidate L1 (a __threadfence() is MEMBAR.SC.GPU + CCTL.IVALL, i.e. an L1 flush of the whole SM per item).
+__device__ __forceinline__ unsigned ticket_release(unsigned* p) {
+  unsigned r;
+  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 // Fused result exchange: executed by the warp that completed factor f.  If f was the LAST factor of its pair, sum the
 // pair's records (fp64, fixed order -> deterministic), and store the fp32 row into every rank's slab (128-bit stores;
 // peers are reached through their IPC-mapped addresses over NVLink).
-__device__ __noinline__ void pair_push(int f, const FactorDesc& D, const double* __restrict__ out, const PeerPush* __restrict__ peer_tab, float* row /* 96 floats of shared memory */) {
+__device__ __noinline__ void pair_push(const FactorDesc& D, const double* __restrict__ out, const PeerPush* __restrict__ peer_tab, float* row /* 96 floats of shared memory */) {
   const PeerPush& peer = *peer_tab;
   const int lane = threadIdx.x & 31;
-  __threadfence();  // this factor's record is visible before the ticket
-  __syncwarp();
+  __syncwarp();  // this factor's record (written by all lanes) happens-before the release below
   int last = 0;
   const int pb = peer.pair_ptr[D.pair], pe = peer.pair_ptr[D.pair + 1];
   if (lane == 0) {
-    const unsigned t = atomicAdd(&peer.pair_done[D.pair], 1u);
+    const unsigned t = ticket_release(&peer.pair_done[D.pair]);
     last = (t == (unsigned)(pe - pb) - 1u);
     if (last) peer.pair_done[D.pair] = 0u;
   }
   last = __shfl_sync(0xffffffffu, last, 0);
   if (!last) return;
-  __threadfence();
+  fence_acquire();
   for (int e = lane; e < GB_SLAB_STRIDE; e += 32) {
     double s = 0.0;
     if (e < 92) {
@@ -143,16 +230,17 @@ __device__ __noinline__ void pair_push(int f, const FactorDesc& D, const double*
     const float4 v = reinterpret_cast<const float4*>(row)[lane];
     for (int p = 0; p < peer.world; p++) reinterpret_cast<float4*>(peer.base[p] + (size_t)D.pair * GB_SLAB_STRIDE)[lane] = v;
   }
-  (void)f;
 }
 
-__device__ void factor_epilogue(int f, const FactorDesc& D, const double* __restrict__ poses, double* __restrict__ accum, int acc_slots, double* __restrict__ out, float* __restrict__ slab, double* sm /* >= 36+36+36+32 doubles */) {
+// fp64 epilogue of one factor, executed (all 32 lanes in parallel) by the warp that retired the factor's last item.
+// sm: >= 104 doubles of shared memory (A[32] | Ad[36] | X[36]).
+constexpr int kEpilogueDoubles = 104;
+__device__ __noinline__ void factor_epilogue(int f, const FactorDesc& D, const double* __restrict__ poses, double* __restrict__ accum, int acc_slots, double* __restrict__ out, float* __restrict__ slab, double* sm) {
   const int lane = threadIdx.x & 31;
-  double* A = sm;            // 32 accumulators
-  double* H = sm + 32;       // 6x6 H_tt, row-major (symmetric)
-  double* Ad = sm + 68;      // 6x6 adjoint, row-major
-  double* X = sm + 104;      // H_tt * Ad, row-major
-  // the accumulators were produced by L2 atomics of other CTAs: read them past L1
+  double* A = sm;        // 32 accumulators
+  double* Ad = sm + 32;  // 6x6 adjoint, row-major
+  double* X = sm + 68;   // H_tt * Ad, row-major
+  // the accumulators were produced by L2 reductions of other CTAs: read them past L1
   // (a factor's accumulator is replicated over acc_slots copies so that the items of a sweep with FEW factors do not all
   //  serialise on the same 29 addresses in L2; summed here in slot order)
   if (lane < 29) {
@@ -164,30 +252,33 @@ __device__ void factor_epilogue(int f, const FactorDesc& D, const double* __rest
     }
     A[lane] = a;
   }
-  __syncwarp();
-  // unpack upper triangle
-  if (lane == 0) {
-    int k = 0;
-    for (int i = 0; i < 6; i++)
-      for (int j = i; j < 6; j++) { H[i * 6 + j] = A[k]; H[j * 6 + i] = A[k]; k++; }
-    // Ad = [[R, 0], [hat(t) R, R]] from the fp32-cast pose the kernel used
-    const double* T = poses + (size_t)f * 16;
-    double R[9], t[3];
-    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) R[r * 3 + c] = (double)(float)T[c * 4 + r]; t[r] = (double)(float)T[12 + r]; }
-    const double ht[9] = {0, -t[2], t[1], t[2], 0, -t[0], -t[1], t[0], 0};
-    for (int i = 0; i < 36; i++) Ad[i] = 0.0;
-    for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) {
-        Ad[i * 6 + j] = R[i * 3 + j];
-        Ad[(i + 3) * 6 + (j + 3)] = R[i * 3 + j];
-        Ad[(i + 3) * 6 + j] = ht[i * 3 + 0] * R[0 * 3 + j] + ht[i * 3 + 1] * R[1 * 3 + j] + ht[i * 3 + 2] * R[2 * 3 + j];
+  // Ad = [[R, 0], [hat(t) R, R]] from the fp32-cast pose the kernel used
+  const double* T = poses + (size_t)f * 16;
+  for (int e = lane; e < 36; e += 32) {
+    const int i = e / 6, j = e % 6;
+    double v = 0.0;
+    if (j < 3 || i >= 3) {
+      const int ri = i % 3, cj = j % 3;
+      if ((i < 3) == (j < 3)) {
+        v = (double)(float)T[cj * 4 + ri];  // R(ri, cj)
+      } else {  // i >= 3, j < 3: (hat(t) R)(ri, cj) = (t x R(:, cj))(ri)
+        const double t0 = (double)(float)T[12], t1 = (double)(float)T[13], t2 = (double)(float)T[14];
+        const double r0 = (double)(float)T[cj * 4 + 0], r1 = (double)(float)T[cj * 4 + 1], r2 = (double)(float)T[cj * 4 + 2];
+        v = ri == 0 ? t1 * r2 - t2 * r1 : (ri == 1 ? t2 * r0 - t0 * r2 : t0 * r1 - t1 * r0);
       }
+    }
+    Ad[e] = v;
   }
   __syncwarp();
+  // H(i, j) = A[index of (min, max) in the row-major upper triangle]
+  auto H = [&](int i, int j) -> double {
+    const int a = i < j ? i : j, b = i < j ? j : i;
+    return A[a * 6 - (a * (a - 1)) / 2 + (b - a)];
+  };
   for (int e = lane; e < 36; e += 32) {
     const int i = e / 6, j = e % 6;
     double s = 0;
-    for (int k = 0; k < 6; k++) s += H[i * 6 + k] * Ad[k * 6 + j];
+    for (int k = 0; k < 6; k++) s += H(i, k) * Ad[k * 6 + j];
     X[e] = s;
   }
   __syncwarp();
@@ -197,14 +288,15 @@ __device__ void factor_epilogue(int f, const FactorDesc& D, const double* __rest
     const int i = e / 6, j = e % 6;  // output element (row i, col j), stored column-major
     double ss = 0;
     for (int k = 0; k < 6; k++) ss += Ad[k * 6 + i] * X[k * 6 + j];
-    o[j * 6 + i] = H[i * 6 + j];             // H_tt
+    const double hij = H(i, j);
+    o[j * 6 + i] = hij;                      // H_tt
     o[36 + j * 6 + i] = ss;                  // H_ss = Ad^T H_tt Ad
     o[72 + j * 6 + i] = -X[i * 6 + j];       // H_ts = -H_tt Ad
     if (srow) {
       atomicAdd(&srow[21 + j * 6 + i], (float)(-X[i * 6 + j]));
       if (j >= i) {
         const int u = i * 6 - (i * (i - 1)) / 2 + (j - i);  // index in the row-major upper triangle
-        atomicAdd(&srow[u], (float)H[i * 6 + j]);
+        atomicAdd(&srow[u], (float)hij);
         atomicAdd(&srow[57 + u], (float)ss);
       }
     }
@@ -218,41 +310,313 @@ __device__ void factor_epilogue(int f, const FactorDesc& D, const double* __rest
   }
   if (lane == 6) { o[120] = A[27]; if (srow) atomicAdd(&srow[90], (float)A[27]); }
   if (lane == 7) { o[121] = A[28]; if (srow) atomicAdd(&srow[91], (float)A[28]); }
+  __syncwarp();
 }
 
-// ---------------------------------------------------------------------------------------------
-// The sweep kernel.  Persistent grid of independent WARPS: every warp starts on the item with its own
-// index and then draws further work items from a global queue (one atomic per item; the counter is
-// monotonic across launches so it never needs a reset; sweeps with no more items than warps use no
-// queue at all).  An item = up to `chunk` consecutive source points of one factor, processed in rounds of
-// kSubMax points with two warp-local phases:
-//   A (lookup, all lanes busy): 16-byte read of (x, y, z, c00), transform, voxel coordinate, hash
-//     probe (4 points per lane in flight); hits are COMPACTED into the warp's shared-memory queue as (point, voxel) pairs with
-//     ballot + popc, in point order (deterministic).
-//   B (derivatives, dense): lanes walk the queue, so the warp stays full whatever the inlier rate;
-//     only hits pay for the remaining 20 bytes of the source point, the 48-byte voxel record and
-//     the ~180-instruction Mahalanobis / Hessian update.
-// This is the reference's lookup-pass / compaction / derivative-pass structure, but the inlier list
-// lives in shared memory for the lifetime of one round instead of making a round trip through HBM.
-// There is no block-level synchronisation anywhere: the item ends with a transposing warp
-// reduce-scatter (31 shuffles) and 29 fp64 atomics into the factor's accumulator; the warp that
-// retires a factor's last item runs its fp64 epilogue.
-// ---------------------------------------------------------------------------------------------
+// =============================================================================================
+// k_vgicp_sweep4 -- bulk-async staged source tiles, lazy release tickets, carry-over hit queue
+// =============================================================================================
+//
+// Per warp, in dynamic shared memory:
+//   two stage buffers { float4 p0[T + 32]; float4 p1[T + 32]; float p2[T + 32]; }  -- the three planes of up to T consecutive
+//       source points, filled by three cp.async.bulk (1-D TMA) copies that complete on the buffer's mbarrier; the last
+//       32 slots of every plane are the CARRY area (see below);
+//   a hit queue uint2 q[T + 32] = (slot in the current stage buffer, voxel index).
+// The stream of stages of a warp (the stages of its items, one item after the other) is double buffered: while stage s is
+// being processed, the copy of stage s + 1 -- possibly the first stage of the NEXT item, whose identity is known one item
+// ahead -- is in flight.  Nothing in the lookup phase waits for a global load of the source cloud any more, and the
+// derivative phase reads the point from shared memory instead of gathering 36 bytes from L2.
+//   phase A (lookup, all lanes): LDS {x,y,z,c00} -> transform -> voxel coordinate -> hash -> first two buckets (LDG.128 x2,
+//       T/32 points per lane in flight) -> compaction of the hits into q with ballot + popc, in point order.
+//   phase B (derivatives): lanes walk q in groups of 32.  Only FULL groups are processed; the < 32 left-over hits are
+//       copied (36 bytes each) into the carry area of the OTHER stage buffer and head the queue of the next stage, so the
+//       ~200-instruction derivative pass always runs with 32 active lanes whatever the inlier rate.  The last stage of an
+//       item flushes the partial group.
+// Item end: transposing warp reduce-scatter (31 shuffles), 29 fp64 REDs into the factor's accumulator.  The ticket that
+// counts the factor's finished items is published LAZILY with a release atomic (no fence, no L1 invalidation): while the
+// first bucket loads of the warp's next item are in flight, the MEMBAR that the release implies waits for nothing that
+// the warp was not going to wait for anyway.  The warp that draws a factor's last ticket runs the epilogue (acquire fence
+// there only) at the end of the item in which it found out.
+template <int T>
+struct StageBuf {
+  float4 p0[T + 32];
+  float4 p1[T + 32];
+  float p2[T + 32];
+};
+template <int T>
+struct WarpSmem {
+  StageBuf<T> buf[2];
+  uint2 q[T + 32];
+  unsigned long long mbar[2];
+};
+constexpr int kDescCache = 40;  // factors whose descriptor + fp32 pose are cached in shared memory (an odometry graph has <= 34)
+struct CtaCache {
+  FactorDesc desc[kDescCache];
+  PoseF pose[kDescCache];
+  PoseF pose_eval[kDescCache];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+    "{\n"
+    ".reg .pred P1;\n"
+    "LAB_WAIT:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+    "@P1 bra DONE;\n"
+    "bra LAB_WAIT;\n"
+    "DONE:\n"
+    "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// lane 0: start the copy of `cnt` points [first, first + cnt) of a cloud into stage buffer `sb`
+template <int T>
+__device__ __forceinline__ void issue_stage(StageBuf<T>* sb, uint32_t bar, const float4* p0, const float4* p1, const float* p2, int first, int cnt) {
+  const uint32_t b0 = (uint32_t)cnt * 16u, b2 = ((uint32_t)cnt * 4u + 15u) & ~15u;  // the p2 plane is padded to 256 B: reading <= 12 B past the item is safe
+  mbar_expect_tx(bar, 2u * b0 + b2);
+  bulk_g2s(smem_u32(sb->p0), p0 + first, b0, bar);
+  bulk_g2s(smem_u32(sb->p1), p1 + first, b0, bar);
+  bulk_g2s(smem_u32(sb->p2), p2 + first, b2, bar);
+}
+
+template <int MODE, int T, bool PEER, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep4(
+  const FactorDesc* __restrict__ descs, int num_factors, const double* __restrict__ poses, const double* __restrict__ poses_eval,
+  const int2* __restrict__ items, int num_items, int chunk,
+  unsigned long long* __restrict__ item_ctr, unsigned long long ctr_base,
+  double* __restrict__ accum, int acc_slots, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab, const PeerPush* __restrict__ peer) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int U = T / 32;  // points per lane per stage
+  static_assert(sizeof(StageBuf<T>) >= (kEpilogueDoubles * 8 + GB_SLAB_STRIDE * 4), "a stage buffer doubles as the epilogue scratch");
+  WarpSmem<T>* const ws_all = reinterpret_cast<WarpSmem<T>*>(smem_raw);
+  CtaCache* const cache = reinterpret_cast<CtaCache*>(smem_raw + sizeof(WarpSmem<T>) * kWarps);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  WarpSmem<T>& ws = ws_all[warp];
+  uint2* __restrict__ q = ws.q;
+  const uint32_t bar0 = smem_u32(&ws.mbar[0]), bar1 = smem_u32(&ws.mbar[1]);
+
+  // ---- CTA prologue: descriptor / pose cache (small factor sets), mbarriers ----
+  const bool cached = num_factors <= kDescCache;
+  if (cached) {
+    for (int f = threadIdx.x; f < num_factors; f += kThreads) {
+      cache->desc[f] = descs[f];
+      cache->pose[f] = pose_from_colmajor(poses + (size_t)f * 16);
+      if (MODE == GB_MODE_ERROR) cache->pose_eval[f] = pose_from_colmajor(poses_eval + (size_t)f * 16);
+    }
+  }
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();  // the only block-level barrier of the kernel
+
+  const int total_warps = gridDim.x * kWarps;
+  const bool dynamic = num_items > total_warps;
+  int item = blockIdx.x * kWarps + warp;  // first item: static
+  if (item >= num_items) return;
+  // second item: drawn now so that its identity is known one item ahead (its first stage is prefetched during the current item)
+  int nxt = 0x7fffffff;
+  if (dynamic) {
+    if (lane == 0) nxt = (int)(atomicAdd(item_ctr, 1ull) - ctr_base) + total_warps;
+    nxt = __shfl_sync(0xffffffffu, nxt, 0);
+  }
+
+  auto desc_of = [&](int f) -> const FactorDesc* { return cached ? &cache->desc[f] : &descs[f]; };
+  // lane 0: start the copy of the first stage of item `it_idx` into buffer `b` (the item itself is re-read at its start)
+  auto prefetch_item = [&](int it_idx, int b) {
+    const int2 it = __ldg(&items[it_idx]);
+    const FactorDesc* dp = desc_of(it.x);
+    const int cnt = min(min(chunk, dp->n - it.y), T);
+    if (cnt > 0) issue_stage<T>(&ws.buf[b], b ? bar1 : bar0, dp->p0, dp->p1, dp->p2, it.y, cnt);
+  };
+  // lane 0 (after a __syncwarp): publish the ticket of the previous item's factor; is that factor complete now?
+  auto publish = [&](int pf) -> int {
+    const unsigned t = ticket_release(&done[pf]);
+    const int last = (t == (unsigned)desc_of(pf)->num_tiles - 1u);
+    if (last) done[pf] = 0u;  // self-cleaning: nobody draws this ticket again in this launch
+    return last;
+  };
+
+  int cur = 0;                   // stage buffer of the next stage to be processed
+  uint32_t par0 = 0, par1 = 0;   // mbarrier phase parities
+  if (lane == 0) prefetch_item(item, 0);
+  int pend_f = -1;               // factor of the previous item: its ticket has not been published yet
+  int pend_last = 0;             // (lane 0) the previous item turned out to be its factor's last
+
+  while (true) {
+    int nxt2 = 0x7fffffff;
+    if (dynamic && lane == 0) nxt2 = (int)(atomicAdd(item_ctr, 1ull) - ctr_base) + total_warps;  // consumed at the end of the item
+    const int2 it = __ldg(&items[item]);
+    const int f = it.x;
+    const FactorDesc* const dp = desc_of(f);
+    // only what the lookup / derivative phases need stays in registers; the plane pointers are re-read by lane 0 when it
+    // issues a copy
+    FactorDesc D;
+    D.buckets = dp->buckets; D.voxels = dp->voxels; D.mask = dp->mask; D.max_scan = dp->max_scan; D.inv_res = dp->inv_res;
+    const PoseF P = cached ? cache->pose[f] : pose_from_colmajor(poses + (size_t)f * 16);
+    PoseF Pe = P;
+    if (MODE == GB_MODE_ERROR) Pe = cached ? cache->pose_eval[f] : pose_from_colmajor(poses_eval + (size_t)f * 16);
+    const int item_end = min(it.y + chunk, dp->n);
+    const int nstages = (max(0, item_end - it.y) + T - 1) / T;  // 0: factor without points (its epilogue still runs)
+
+    float acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) acc[k] = 0.f;
+    int nq = 0;  // warp-uniform queue length (carried hits first)
+    bool published = (pend_f < 0);
+
+    if (nstages == 0 && lane == 0 && nxt < num_items) prefetch_item(nxt, cur);
+    for (int s = 0; s < nstages; s++) {
+      const int wb = it.y + s * T;
+      const int cnt = min(T, item_end - wb);
+      const bool last_stage = (s == nstages - 1);
+      // ---- keep the copy engine one stage ahead ----
+      if (lane == 0) {
+        if (!last_stage) issue_stage<T>(&ws.buf[cur ^ 1], (cur ^ 1) ? bar1 : bar0, dp->p0, dp->p1, dp->p2, wb + T, min(T, item_end - wb - T));
+        else if (nxt < num_items) prefetch_item(nxt, cur ^ 1);
+      }
+      StageBuf<T>& sb = ws.buf[cur];
+      StageBuf<T>& ob = ws.buf[cur ^ 1];
+      mbar_wait(cur ? bar1 : bar0, cur ? par1 : par0);
+      if (cur) par1 ^= 1u; else par0 ^= 1u;
+
+      // ---------------- phase A: lookup + compaction ----------------
+      {
+        int cx[U], cy[U], cz[U];
+        uint32_t h[U];
+        int4 b[U], b1[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (u * 32 < cnt) {  // warp-uniform: rows beyond the stage's points are skipped
+            const float4 a0 = sb.p0[u * 32 + lane];
+            float qx, qy, qz;
+            transform(P, a0.x, a0.y, a0.z, qx, qy, qz);
+            cx[u] = gb_coord(qx, D.inv_res); cy[u] = gb_coord(qy, D.inv_res); cz[u] = gb_coord(qz, D.inv_res);
+            // a NaN coordinate converts to 0 and would probe voxel (0, ., .): force a coordinate no voxel can have (|c| < 2^20)
+            const float sum = (qx + qy) + qz;
+            if (!(sum == sum)) cx[u] = 0x7fffffff;
+            h[u] = gb_hash(cx[u], cy[u], cz[u]);
+            b[u] = __ldg(&D.buckets[h[u] & D.mask]);
+            b1[u] = __ldg(&D.buckets[(h[u] + 1u) & D.mask]);
+          }
+        }
+        // the previous item's ticket: its REDs were issued a stage ago, and the MEMBAR of the release overlaps with the
+        // bucket loads above
+        if (!published) {
+          published = true;
+          __syncwarp();
+          if (lane == 0) pend_last = publish(pend_f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (u * 32 < cnt) {
+            int v = resolve_probe(D, b[u], b1[u], h[u], cx[u], cy[u], cz[u]);
+            if (u * 32 + lane >= cnt) v = -1;
+            const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
+            if (v >= 0) q[nq + __popc(m & lt_mask)] = make_uint2((unsigned)(u * 32 + lane), (unsigned)v);
+            nq += __popc(m);
+          }
+        }
+      }
+      __syncwarp();
+
+      // ---------------- phase B: derivative pass over full groups of 32 hits ----------------
+      const int nproc = last_stage ? nq : (nq & ~31);
+#pragma unroll 1
+      for (int k = lane; k < nproc; k += 32) {
+        const uint2 e = q[k];
+        const float4 v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]);
+        const float4 v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]);
+        const float4 v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
+        accumulate_hit<MODE>(acc, Pe, sb.p0[e.x], sb.p1[e.x], sb.p2[e.x], v0, v1, v2);
+      }
+      // ---------------- carry the partial group over to the next stage ----------------
+      if (!last_stage) {
+        const int rem = nq - nproc;
+        uint2 e = make_uint2(0u, 0u);
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+        float c2 = 0.f;
+        if (lane < rem) {
+          e = q[nproc + lane];
+          c0 = sb.p0[e.x]; c1 = sb.p1[e.x]; c2 = sb.p2[e.x];
+        }
+        __syncwarp();
+        if (lane < rem) {
+          ob.p0[T + lane] = c0; ob.p1[T + lane] = c1; ob.p2[T + lane] = c2;
+          q[lane] = make_uint2((unsigned)(T + lane), e.y);
+        }
+        nq = rem;
+      }
+      __syncwarp();  // every lane is done with this stage buffer and the queue before the next copy / compaction
+      cur ^= 1;
+    }
+    if (!published) {  // item without a lookup phase (empty factor)
+      __syncwarp();
+      if (lane == 0) pend_last = publish(pend_f);
+    }
+
+    // ---------------- item reduction: warp -> 29 fp64 reductions ----------------
+    double* __restrict__ my_acc = accum + ((size_t)f * acc_slots + (size_t)(item & (acc_slots - 1))) * GB_ACC_STRIDE;
+    if (MODE == GB_MODE_LINEARIZE) {
+      const float r = warp_reduce_scatter32(acc, lane);
+      if (lane < 29) atomicAdd(&my_acc[lane], (double)r);
+    } else {
+      float e = acc[27], n = acc[28];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) { e += __shfl_xor_sync(0xffffffffu, e, o); n += __shfl_xor_sync(0xffffffffu, n, o); }
+      if (lane == 27) atomicAdd(&my_acc[27], (double)e);
+      if (lane == 28) atomicAdd(&my_acc[28], (double)n);
+    }
+
+    // ---------------- epilogue of the PREVIOUS item's factor, if that item was its last ----------------
+    // scratch: the stage buffer that was consumed last (the other one may be receiving the next item's first stage)
+    if (pend_f >= 0 && __shfl_sync(0xffffffffu, pend_last, 0)) {
+      fence_acquire();
+      const FactorDesc Dp = *desc_of(pend_f);
+      double* scratch = reinterpret_cast<double*>(&ws.buf[cur ^ 1]);
+      factor_epilogue(pend_f, Dp, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, acc_slots, out, slab, scratch);
+      if (PEER && MODE == GB_MODE_LINEARIZE) pair_push(Dp, out, peer, reinterpret_cast<float*>(scratch + kEpilogueDoubles));
+      __syncwarp();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes of the scratch before the next bulk copy into it
+    }
+    pend_f = f;
+    pend_last = 0;
+
+    item = nxt;
+    nxt = __shfl_sync(0xffffffffu, nxt2, 0);
+    if (item >= num_items) break;
+  }
+
+  // ---- drain: publish the last item's ticket ----
+  __syncwarp();
+  if (lane == 0) pend_last = publish(pend_f);
+  if (__shfl_sync(0xffffffffu, pend_last, 0)) {
+    fence_acquire();
+    const FactorDesc Dp = *desc_of(pend_f);
+    double* scratch = reinterpret_cast<double*>(&ws.buf[cur ^ 1]);
+    factor_epilogue(pend_f, Dp, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, acc_slots, out, slab, scratch);
+    if (PEER && MODE == GB_MODE_LINEARIZE) pair_push(Dp, out, peer, reinterpret_cast<float*>(scratch + kEpilogueDoubles));
+  }
+}
+
+// =============================================================================================
+// k_vgicp_sweep3 -- the round-1 kernel (register-staged loads; fence + ticket per item).  GB_KERNEL=3.
+// =============================================================================================
 constexpr int kSubMax = 512;   // queue capacity per warp (points per round)
 constexpr int kLookupUnroll = 4;
 
-__device__ __forceinline__ PoseF pose_from_colmajor(const double* __restrict__ T) {
-  PoseF P;
-  P.r00 = (float)T[0]; P.r01 = (float)T[4]; P.r02 = (float)T[8];  P.tx = (float)T[12];
-  P.r10 = (float)T[1]; P.r11 = (float)T[5]; P.r12 = (float)T[9];  P.ty = (float)T[13];
-  P.r20 = (float)T[2]; P.r21 = (float)T[6]; P.r22 = (float)T[10]; P.tz = (float)T[14];
-  return P;
-}
-
-template <int MODE, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
+template <int MODE, bool PEER>
+__global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep3(
   const FactorDesc* __restrict__ descs, const double* __restrict__ poses, const double* __restrict__ poses_eval,
-  const int2* __restrict__ items, int num_items, int chunk, int static_first,
+  const int2* __restrict__ items, int num_items, int chunk,
   unsigned long long* __restrict__ item_ctr, unsigned long long ctr_base,
   double* __restrict__ accum, int acc_slots, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab, const PeerPush* __restrict__ peer) {
   __shared__ __align__(16) uint2 s_q[kWarps][kSubMax];
@@ -260,15 +624,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
   const unsigned lt_mask = (1u << lane) - 1u;
   uint2* __restrict__ q = s_q[warp];
 
-  // first item: static (warp id) -- thousands of warps hammering one atomic at kernel start cost ~10 us, which is most of
-  // a small odometry sweep; further items (only when there are more items than warps) come from the global queue
-  const int total_warps = static_first ? gridDim.x * kWarps : 0;
+  // first item: static (warp id); further items (only when there are more items than warps) come from the global queue
+  const int total_warps = gridDim.x * kWarps;
   const bool dynamic = num_items > total_warps;
   int item = blockIdx.x * kWarps + warp;
-  if (!static_first) {
-    if (lane == 0) item = (int)(atomicAdd(item_ctr, 1ull) - ctr_base);
-    item = __shfl_sync(0xffffffffu, item, 0);
-  }
 
   while (item < num_items) {
     int next_item = 0x7fffffff;
@@ -276,7 +635,6 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
     const int2 it = __ldg(&items[item]);
     const int f = it.x;
     const FactorDesc D = descs[f];
-    // pose -> fp32 row-major R | t  (Isometry3f cast of the reference GPU factor)
     const PoseF P = pose_from_colmajor(poses + (size_t)f * 16);
     PoseF Pe = P;
     if (MODE == GB_MODE_ERROR) Pe = pose_from_colmajor(poses_eval + (size_t)f * 16);
@@ -288,7 +646,6 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
 
     for (int wb = it.y; wb < item_end; wb += kSubMax) {
       const int we = min(wb + kSubMax, item_end);
-      // ---------------- phase A: lookup + compaction ----------------
       int nq = 0;  // warp-uniform queue length
       for (int i0 = wb; i0 < we; i0 += 32 * kLookupUnroll) {
         int cx[kLookupUnroll], cy[kLookupUnroll], cz[kLookupUnroll];
@@ -301,31 +658,16 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
           float qx, qy, qz;
           transform(P, a0.x, a0.y, a0.z, qx, qy, qz);
           cx[u] = gb_coord(qx, D.inv_res); cy[u] = gb_coord(qy, D.inv_res); cz[u] = gb_coord(qz, D.inv_res);
+          const float sum = (qx + qy) + qz;
+          if (!(sum == sum)) cx[u] = 0x7fffffff;  // NaN point: a coordinate no voxel has
           h[u] = gb_hash(cx[u], cy[u], cz[u]);
-          // the first two probe slots travel together (adjacent 16-byte buckets, one round trip): measured +5 % over
-          // fetching the second slot on demand even with tables at load <= 1/8
           b[u] = __ldg(&D.buckets[h[u] & D.mask]);
           b1[u] = __ldg(&D.buckets[(h[u] + 1u) & D.mask]);
         }
 #pragma unroll
         for (int u = 0; u < kLookupUnroll; u++) {
           const int i = i0 + u * 32 + lane;
-          int v = -1;
-          if (b[u].w >= 0) {
-            if (b[u].x == cx[u] && b[u].y == cy[u] && b[u].z == cz[u]) {
-              v = b[u].w;
-            } else if (D.max_scan > 1 && b1[u].w >= 0) {
-              if (b1[u].x == cx[u] && b1[u].y == cy[u] && b1[u].z == cz[u]) {
-                v = b1[u].w;
-              } else {
-                for (int k = 2; k < D.max_scan; k++) {  // rare: longer collision chain
-                  const int4 bb = __ldg(&D.buckets[(h[u] + (uint32_t)k) & D.mask]);
-                  if (bb.w < 0) break;
-                  if (bb.x == cx[u] && bb.y == cy[u] && bb.z == cz[u]) { v = bb.w; break; }
-                }
-              }
-            }
-          }
+          int v = resolve_probe(D, b[u], b1[u], h[u], cx[u], cy[u], cz[u]);
           if (i >= we) v = -1;
           const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
           if (v >= 0) q[nq + __popc(m & lt_mask)] = make_uint2((unsigned)i, (unsigned)v);
@@ -333,8 +675,6 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
         }
       }
       __syncwarp();
-
-      // ---------------- phase B: dense derivative pass over the round's inliers ----------------
 #pragma unroll 2
       for (int k = lane; k < nq; k += 32) {
         const uint2 e = q[k];
@@ -345,43 +685,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
         const float4 v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]);
         const float4 v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]);
         const float4 v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
-        float qx, qy, qz;
-        transform(Pe, a0.x, a0.y, a0.z, qx, qy, qz);
-        float mxx, mxy, mxz, myy, myz, mzz;
-        fused_mahalanobis(Pe, a0.w, a1.x, a1.y, a1.z, a1.w, a2, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, mxx, mxy, mxz, myy, myz, mzz);
-        const float rx = v0.x - qx, ry = v0.y - qy, rz = v0.z - qz;
-        const float wx = mxx * rx + mxy * ry + mxz * rz;
-        const float wy = mxy * rx + myy * ry + myz * rz;
-        const float wz = mxz * rx + myz * ry + mzz * rz;
-        acc[27] += rx * wx + ry * wy + rz * wz;
-        acc[28] += 1.0f;
-        if (MODE == GB_MODE_LINEARIZE) {
-          // G = hat(q) M   (rows: rotation, cols: translation block of H_tt)
-          const float g00 = qy * mxz - qz * mxy, g01 = qy * myz - qz * myy, g02 = qy * mzz - qz * myz;
-          const float g10 = qz * mxx - qx * mxz, g11 = qz * mxy - qx * myz, g12 = qz * mxz - qx * mzz;
-          const float g20 = qx * mxy - qy * mxx, g21 = qx * myy - qy * mxy, g22 = qx * myz - qy * mxz;
-          // H_rr = G hat(q)^T : row i = q x g_i   (upper triangle)
-          acc[0] += qy * g02 - qz * g01;
-          acc[1] += qz * g00 - qx * g02;
-          acc[2] += qx * g01 - qy * g00;
-          acc[3] += g00; acc[4] += g01; acc[5] += g02;
-          acc[6] += qz * g10 - qx * g12;
-          acc[7] += qx * g11 - qy * g10;
-          acc[8] += g10; acc[9] += g11; acc[10] += g12;
-          acc[11] += qx * g21 - qy * g20;
-          acc[12] += g20; acc[13] += g21; acc[14] += g22;
-          acc[15] += mxx; acc[16] += mxy; acc[17] += mxz; acc[18] += myy; acc[19] += myz; acc[20] += mzz;
-          // b_t = [q x w ; w]
-          acc[21] += qy * wz - qz * wy;
-          acc[22] += qz * wx - qx * wz;
-          acc[23] += qx * wy - qy * wx;
-          acc[24] += wx; acc[25] += wy; acc[26] += wz;
-        }
+        accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
       }
       __syncwarp();  // the queue is overwritten by the next round
     }
 
-    // ---------------- item reduction: warp -> 29 fp64 atomics ----------------
     double* __restrict__ my_acc = accum + ((size_t)f * acc_slots + (size_t)(item & (acc_slots - 1))) * GB_ACC_STRIDE;
     if (MODE == GB_MODE_LINEARIZE) {
       const float r = warp_reduce_scatter32(acc, lane);
@@ -405,8 +713,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep(
     if (last) {
       __threadfence();
       factor_epilogue(f, D, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, acc_slots, out, slab, reinterpret_cast<double*>(q));
-      __syncwarp();
-      if (MODE == GB_MODE_LINEARIZE && peer != nullptr) pair_push(f, D, out, peer, reinterpret_cast<float*>(q) + 512);
+      if (PEER && MODE == GB_MODE_LINEARIZE) pair_push(D, out, peer, reinterpret_cast<float*>(q) + 512);
       __syncwarp();
     }
     item = __shfl_sync(0xffffffffu, next_item, 0);
@@ -430,6 +737,8 @@ __global__ void __launch_bounds__(256) k_overlap(int num_targets, const FactorDe
       const PoseF P = load_pose(s_poses + 12 * t);
       float qx, qy, qz;
       transform(P, a0.x, a0.y, a0.z, qx, qy, qz);
+      const float sum = (qx + qy) + qz;
+      if (!(sum == sum)) continue;  // NaN point: no voxel
       const float inv_res = descs[t].inv_res;
       const int v = gb_lookup(descs[t].buckets, descs[t].mask, descs[t].max_scan, gb_coord(qx, inv_res), gb_coord(qy, inv_res), gb_coord(qz, inv_res));
       if (v >= 0) { local++; break; }
@@ -442,11 +751,33 @@ __global__ void __launch_bounds__(256) k_overlap(int num_targets, const FactorDe
 
 }  // namespace
 
-template <int MODE, int MINB>
-static void launch_variant(gb_sweep* s, const double* poses_eval, float* slab) {
-  // the table for the buffer of the current step parity (both were written to the device when the slab was attached)
-  const PeerPush* pp = (MODE == GB_MODE_LINEARIZE && s->peer) ? s->d_peer_tables + s->peer->parity : nullptr;
-  k_vgicp_sweep<MODE, MINB><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->static_first, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+template <int T>
+static constexpr size_t sweep4_smem_bytes() { return sizeof(WarpSmem<T>) * kWarps + sizeof(CtaCache); }
+
+size_t gb_sweep4_smem_bytes(int stage_points) { return stage_points == 64 ? sweep4_smem_bytes<64>() : sweep4_smem_bytes<128>(); }
+
+template <int MODE, int T, bool PEER, int MINB>
+static cudaError_t launch4(gb_sweep* s, const double* poses_eval, float* slab, const PeerPush* pp) {
+  static bool attr_set[16] = {};  // per device
+  auto kern = k_vgicp_sweep4<MODE, T, PEER, MINB>;
+  const size_t smem = sweep4_smem_bytes<T>();
+  const int dev = s->ctx->device & 15;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  kern<<<s->grid, kThreads, smem, s->ctx->stream>>>(s->d_descs, (int)s->F, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
+  return cudaGetLastError();
+}
+
+template <int MODE, bool PEER>
+static cudaError_t launch3(gb_sweep* s, const double* poses_eval, float* slab, const PeerPush* pp) {
+  k_vgicp_sweep3<MODE, PEER><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
+  return cudaGetLastError();
 }
 
 // completion flags of the fused exchange: one thread per rank publishes this rank's step to that peer, then waits for the
@@ -463,7 +794,7 @@ __global__ void k_peer_signal_wait(PeerFlags pf, int world, int rank, unsigned s
   const long long t0 = clock64();
   while ((int)(*mine - step) < 0) {
     __nanosleep(200);
-    if (clock64() - t0 > 20000000000ll) { *timeout = 1; break; }  // ~10 s: a peer died; do not hang the GPU
+    if (clock64() - t0 > 4000000000ll) { *timeout = 1; break; }  // ~2 s: a peer died; do not hold the GPU
   }
   __threadfence_system();
 }
@@ -471,21 +802,27 @@ __global__ void k_peer_signal_wait(PeerFlags pf, int world, int rank, unsigned s
 gb_status gb_launch_sweep(gb_sweep* s, int mode) {
   if (s->num_tiles == 0) return GB_OK;
   gb_ctx* ctx = s->ctx;
-  // register-budget variant: 2 CTAs/SM (124 regs, no spills), 3 (80 regs), 4 (64 regs); chosen when the sweep is created
-  const int v = s->min_blocks;
-  if (mode == GB_MODE_LINEARIZE) {
-    if (v >= 4) launch_variant<GB_MODE_LINEARIZE, 4>(s, nullptr, s->d_slab);
-    else if (v == 3) launch_variant<GB_MODE_LINEARIZE, 3>(s, nullptr, s->d_slab);
-    else launch_variant<GB_MODE_LINEARIZE, 2>(s, nullptr, s->d_slab);
+  // the table for the buffer of the current step parity (both were written to the device when the slab was attached)
+  const bool peer = (mode == GB_MODE_LINEARIZE) && s->peer != nullptr;
+  const PeerPush* pp = peer ? s->d_peer_tables + s->peer->parity : nullptr;
+  float* slab = mode == GB_MODE_LINEARIZE ? s->d_slab : nullptr;
+  const double* pe = mode == GB_MODE_ERROR ? s->d_poses_eval : nullptr;
+  cudaError_t e;
+  if (s->kernel_version == 3) {
+    if (mode == GB_MODE_LINEARIZE) e = peer ? launch3<GB_MODE_LINEARIZE, true>(s, pe, slab, pp) : launch3<GB_MODE_LINEARIZE, false>(s, pe, slab, pp);
+    else e = launch3<GB_MODE_ERROR, false>(s, pe, slab, pp);
+  } else if (s->stage_points == 64) {
+    if (mode == GB_MODE_LINEARIZE) e = peer ? launch4<GB_MODE_LINEARIZE, 64, true, 3>(s, pe, slab, pp) : launch4<GB_MODE_LINEARIZE, 64, false, 3>(s, pe, slab, pp);
+    else e = launch4<GB_MODE_ERROR, 64, false, 3>(s, pe, slab, pp);
   } else {
-    if (v >= 4) launch_variant<GB_MODE_ERROR, 4>(s, s->d_poses_eval, nullptr);
-    else if (v == 3) launch_variant<GB_MODE_ERROR, 3>(s, s->d_poses_eval, nullptr);
-    else launch_variant<GB_MODE_ERROR, 2>(s, s->d_poses_eval, nullptr);
+    if (mode == GB_MODE_LINEARIZE) e = peer ? launch4<GB_MODE_LINEARIZE, 128, true, 2>(s, pe, slab, pp) : launch4<GB_MODE_LINEARIZE, 128, false, 2>(s, pe, slab, pp);
+    else e = launch4<GB_MODE_ERROR, 128, false, 2>(s, pe, slab, pp);
   }
-  GB_CUDA(cudaGetLastError());
-  // every processed item draws exactly one ticket from the queue (when the queue is in use at all)
-  if (!s->static_first) s->ctr_base += (unsigned long long)s->num_tiles + (unsigned long long)s->grid * kWarps;
-  else if (s->num_tiles > s->grid * kWarps) s->ctr_base += (unsigned long long)s->num_tiles;
+  if (e != cudaSuccess) { gb_set_error("sweep launch failed: %s", cudaGetErrorString(e)); return GB_ERR_CUDA; }
+  // queue bookkeeping: a sweep with more items than warps draws one ticket per processed item, plus (v4) one per warp for
+  // the one-item look-ahead
+  const unsigned long long warps = (unsigned long long)s->grid * kWarps;
+  if ((unsigned long long)s->num_tiles > warps) s->ctr_base += (s->kernel_version == 3 ? 0ull : warps) + (unsigned long long)s->num_tiles;
   ctx->launches++;
   return GB_OK;
 }

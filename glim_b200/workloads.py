@@ -248,11 +248,11 @@ def _update_keyframes_overlap(w: Workload, keyframes: list, cur: int, p: Odometr
     keyframes.pop(int(np.argmin(scores)))
 
 
-def livox_stress(ctx, n_rays=500_000, use_gpu=False) -> Workload:
+def livox_stress(ctx, n_rays=500_000, use_gpu=False, n_targets=17) -> Workload:
     """M5: one dense MID-360-shaped frame against (2 window frames + 15 keyframes) x 2 levels at 0.1 / 0.2 m."""
     w = Workload("livox_stress", ctx)
     sc = synth.make_hall_scene()
-    n_tgt = 17
+    n_tgt = n_targets
     traj = synth.arc_trajectory(n_tgt + 1, step=0.5)
     for i in range(n_tgt + 1):
         w.host_clouds.append(make_scan(sc, "mid360", traj[i], synth.rng_for(501, i), n_rays=n_rays, ctx=ctx, use_gpu=use_gpu))

@@ -2,8 +2,7 @@
 
 CPU: the oracle's two overloads against an independent numpy / scipy implementation; the product's HOST half
 (gb_deskew_pose_table: time table + pose per slot, needs no device) against the oracle.
-GPU: the kernel (gb_deskew) against the oracle.  The kernel was written after round 1's GPU budget was spent and has never
-run: its test is xfail(strict=False) until it has passed once on a B200."""
+GPU: the kernel (gb_deskew) against the oracle (first passed on the driver's B200 at the end of round 1)."""
 import numpy as np
 import pytest
 
@@ -115,7 +114,6 @@ print("deskew gpu ok")
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="k_deskew was written after round 1's GPU budget was spent; this is its first execution")
 def test_gpu_deskew_matches_oracle():
     """Runs in a subprocess so that a fault in the never-executed kernel cannot poison the CUDA context of the other GPU tests."""
     import os

@@ -357,3 +357,121 @@ def test_full_size_properties(ctx, sensor, n_rays, res):
     xyz1, cov1 = oracle.pack_cloud(P, util.cov_colmajor16(Cv))
     ref, _ = oracle.linearize_gpumap(oracle.GpuMap(xyz0, cov0, res), xyz1, cov1, T)
     check_linearized(whole, ref)
+
+
+# ---------------------------------------------------------------------------------------------- round-2 parity holes
+def test_nan_points_and_singular_covariances_match_oracle(ctx, dev, pair):
+    """Degenerate inputs: a NaN source point must be a MISS (it used to probe voxel (0,0,0)), and a point whose
+    fused covariance is singular (zero source and zero voxel covariance) is skipped and NOT counted, as in the oracle."""
+    P0, C0 = pair["points"][0], pair["covs"][0]
+    P1, C1 = pair["points"][1].copy(), pair["covs"][1].copy()
+    # a target whose voxel at the origin is occupied, so that a NaN -> (0,0,0) probe would hit something
+    P0 = np.concatenate([P0, [[0.1, 0.1, 0.1, 1.0], [0.2, 0.1, 0.3, 1.0]]])
+    C0 = np.concatenate([C0, np.tile(np.diag([1.0, 1.0, 1.0, 0.0]), (2, 1, 1))])
+    P1[5, 0] = np.nan
+    P1[77, :3] = np.nan
+    P1[301, 2] = np.inf
+    T = dev["T_gt"]
+    tgt = gpu.PointCloudGPU.clone(P0, C0, ctx=ctx)
+    src = gpu.PointCloudGPU.clone(P1, C1, ctx=ctx)
+    m = gpu.GaussianVoxelMapGPU(0.5, ctx=ctx).insert(tgt)
+    xyz0, cov0 = oracle.pack_cloud(P0, util.cov_colmajor16(C0))
+    xyz1, cov1 = oracle.pack_cloud(P1, util.cov_colmajor16(C1))
+    ref_map = oracle.GpuMap(xyz0, cov0, 0.5)
+    assert np.array_equal(m.download()[0], ref_map.buckets)
+    got = gpu.IntegratedVGICPFactorGPU(np.eye(4), 1, m, src, ctx=ctx).linearize({1: T})
+    ref, corr = oracle.linearize_gpumap(ref_map, xyz1, cov1, T)
+    assert corr[5] < 0 and corr[77] < 0 and corr[301] < 0
+    assert np.isfinite(got["H_ss"]).all() and np.isfinite(got["b_s"]).all()
+    check_linearized(got, ref)
+    assert gpu.overlap_gpu(m, src, T) == oracle.overlap_gpumap([ref_map], xyz1, [T])
+    # singular fused covariance: zero covariances on both sides for half of the source points
+    Z0 = np.zeros_like(pair["covs"][0])
+    Z1 = pair["covs"][1].copy()
+    Z1[: len(Z1) // 2] = 0.0
+    tgt0 = gpu.PointCloudGPU.clone(pair["points"][0], Z0, ctx=ctx)
+    src0 = gpu.PointCloudGPU.clone(pair["points"][1], Z1, ctx=ctx)
+    m0 = gpu.GaussianVoxelMapGPU(0.5, ctx=ctx).insert(tgt0)
+    x0, c0 = oracle.pack_cloud(pair["points"][0], util.cov_colmajor16(Z0))
+    x1, c1 = oracle.pack_cloud(pair["points"][1], util.cov_colmajor16(Z1))
+    r0 = oracle.GpuMap(x0, c0, 0.5)
+    got0 = gpu.IntegratedVGICPFactorGPU(np.eye(4), 1, m0, src0, ctx=ctx).linearize({1: T})
+    ref0, corr0 = oracle.linearize_gpumap(r0, x1, c1, T)
+    assert (corr0[: len(Z1) // 2] >= 0).sum() > 100  # there ARE correspondences among the singular points ...
+    assert ref0[121] < (corr0 >= 0).sum()  # ... and the oracle does not count them
+    check_linearized(got0, ref0)
+
+
+def test_kernel_generations_agree(ctx, dev, monkeypatch):
+    """k_vgicp_sweep4 (bulk-async staged, default) and k_vgicp_sweep3 (round-1 kernel) on the same factor set: identical
+    inlier counts, blocks equal to fp32 summation-order noise; both stage sizes of the v4 kernel."""
+    maps0 = [gpu.GaussianVoxelMapGPU(r, ctx=ctx).insert(dev["cloud"][0]) for r in (0.25, 0.5)]
+    T = dev["T_gt"]
+    outs = {}
+    for name, env in (("v4_128", {"GB_KERNEL": "4", "GB_STAGE": "128"}), ("v4_64", {"GB_KERNEL": "4", "GB_STAGE": "64"}), ("v3", {"GB_KERNEL": "3"}), ("v4_big_items", {"GB_KERNEL": "4", "GB_TILE": "2048"})):
+        for k in ("GB_KERNEL", "GB_STAGE", "GB_TILE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        facs = [gpu.IntegratedVGICPFactorGPU(0, 1, m, dev["cloud"][1], ctx=ctx) for m in maps0]
+        fs = gpu.NonlinearFactorSetGPU(ctx).add(facs)
+        outs[name] = fs.linearize_deltas(np.stack([T, T]))
+        e = fs.error_deltas(np.stack([T, T]), np.stack([T, T]))
+        assert np.allclose(e, outs[name]["error"], rtol=1e-5)
+    for name in ("v4_64", "v3", "v4_big_items"):
+        for i in range(2):
+            assert outs[name][i]["num_inliers"] == outs["v4_128"][i]["num_inliers"]
+            for k in ("H_tt", "H_ss", "H_ts"):
+                assert util.rel_err(outs[name][i][k], outs["v4_128"][i][k]) < 1e-5, (name, k)
+
+
+def _oracle_check_factors(ctx, w, fset, picks, tol=REL_TOL):
+    """Compare the BATCHED sweep's records for the picked factors of a workload factor set with the oracle."""
+    gf = w.gpu_factors(fset)
+    sw = gpu.Sweep(ctx, gf, pair_index=[f.pair for f in fset.factors])
+    sw.set_poses(fset.deltas)
+    sw.launch()
+    rec = sw.fetch()
+    maps = {}
+    packed = {}
+    worst = 0.0
+    for k in picks:
+        f = fset.factors[k]
+        for c in (f.target, f.source):
+            if c not in packed:
+                packed[c] = oracle.pack_cloud(w.host_clouds[c][0], util.cov_colmajor16(w.host_clouds[c][1]))
+        if (f.target, f.level) not in maps:
+            maps[(f.target, f.level)] = oracle.GpuMap(*packed[f.target], w.resolutions[f.level])
+        ref, _ = oracle.linearize_gpumap(maps[(f.target, f.level)], *packed[f.source], fset.deltas[k])
+        got = gpu.unpack_linearized(rec[k])
+        check_linearized(got, ref, tol)
+        worst = max(worst, util.rel_err(got["H_ss"], oracle.split122(ref)["H_ss"]))
+    return sw, rec, worst
+
+
+def test_global_mapping_factors_match_oracle(ctx):
+    """M4 data distribution at full submap size (50 k points, 0.5 / 1.0 m voxels, ~35 % inliers) on a short loop: the batched
+    sweep runs through the dynamic item queue (items > warps) and replicated accumulators; picked factors vs the oracle."""
+    from glim_b200 import workloads
+
+    w = workloads.global_mapping(ctx, n_submaps=12, laps=1, side=60.0, use_gpu=True)
+    fset = w.sets[0]
+    assert len(fset.factors) >= 10 and min(len(c[0]) for c in w.host_clouds) == 50000
+    rng = np.random.default_rng(5)
+    picks = sorted(rng.choice(len(fset.factors), 6, replace=False).tolist())
+    sw, rec, worst = _oracle_check_factors(ctx, w, fset, picks)
+    assert sw.num_tiles > sw.grid * 8  # the queue path
+    inl = rec["num_inliers"] / 50000.0
+    assert 0.05 < np.median(inl) < 0.9
+
+
+def test_livox_dense_factor_matches_oracle(ctx):
+    """M5 shape: 500 k-point MID-360-like clouds, 0.1 / 0.2 m voxels (tables of ~10^6 buckets): both levels of one pair."""
+    from glim_b200 import workloads
+
+    w = workloads.livox_stress(ctx, n_rays=500_000, use_gpu=True, n_targets=2)
+    fset = w.sets[0]
+    assert len(w.host_clouds[0][0]) > 400_000
+    picks = [k for k, f in enumerate(fset.factors) if f.target == 0]
+    assert len(picks) == 2
+    _oracle_check_factors(ctx, w, fset, picks)
