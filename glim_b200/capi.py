@@ -15,7 +15,8 @@ SO_PATH = os.path.join(_HERE, "libglim_b200.so")
 SYMBOLS = [
     "gb_status_string", "gb_last_error", "gb_device_count", "gb_mem_info",
     "gb_ctx_create", "gb_ctx_create_on_stream", "gb_ctx_destroy", "gb_ctx_synchronize", "gb_ctx_stream", "gb_ctx_kernel_launches",
-    "gb_cloud_upload", "gb_cloud_size", "gb_cloud_download", "gb_cloud_destroy",
+    "gb_cloud_upload", "gb_cloud_size", "gb_cloud_download", "gb_cloud_device_ptrs", "gb_cloud_destroy",
+    "gb_hessian_blocks", "gb_slab_row_hessian_blocks",
     "gb_voxelmap_build", "gb_voxelmap_info", "gb_voxelmap_download", "gb_voxelmap_destroy",
     "gb_vgicp_factor_create", "gb_vgicp_factor_destroy", "gb_vgicp_linearize", "gb_vgicp_error",
     "gb_factor_set_linearize", "gb_factor_set_error",
@@ -65,6 +66,9 @@ def lib():
     L.gb_cloud_size.argtypes = [vp, vp]
     L.gb_cloud_download.argtypes = [vp, vp, vp]
     L.gb_cloud_destroy.argtypes = [vp]
+    L.gb_cloud_device_ptrs.argtypes = [vp, vp, vp, vp, vp]
+    L.gb_hessian_blocks.argtypes = [vp, f64, vp, vp, vp, vp, vp, vp]
+    L.gb_slab_row_hessian_blocks.argtypes = [vp, f64, vp, vp, vp, vp, vp, vp, vp]
     L.gb_voxelmap_build.argtypes = [vp, vp, f32, i32, i32, f64, vp]
     L.gb_voxelmap_info.argtypes = [vp, vp, vp, vp]
     L.gb_voxelmap_download.argtypes = [vp, vp, vp, vp, vp]

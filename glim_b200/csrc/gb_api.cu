@@ -78,6 +78,7 @@ static gb_status ctx_create(int device, cudaStream_t stream, bool own, gb_ctx** 
   c->scratch = nullptr; c->scratch_cap = 0;
   c->pinned = nullptr; c->pinned_cap = 0;
   c->launches = 0;
+  c->refs.store(1);
   *out = c;
   return GB_OK;
 }
@@ -85,19 +86,35 @@ extern "C" gb_status gb_ctx_create(int device, gb_ctx** out) { return ctx_create
 extern "C" gb_status gb_ctx_create_on_stream(int device, void* cuda_stream, gb_ctx** out) { return ctx_create(device, (cudaStream_t)cuda_stream, false, out); }
 
 static void sweep_free(gb_sweep* s);
+// Cross links factor <-> sweep (a factor may sit in cached sweeps of several contexts): guarded by one registry mutex.
+static std::mutex g_registry_mu;
+static std::atomic<uint64_t> g_next_factor_id{1};
 
-extern "C" gb_status gb_ctx_destroy(gb_ctx* ctx) {
-  if (!ctx) return GB_OK;
+// Contexts are reference counted: factors, sweeps and peer slabs hold one; gb_ctx_destroy drops the owner's.  A module may
+// therefore destroy its CUDAStream while factors created on it are still alive (member destruction order, thread exit).
+static void ctx_retain(gb_ctx* ctx) { ctx->refs.fetch_add(1); }
+static void ctx_release(gb_ctx* ctx) {
+  if (ctx->refs.fetch_sub(1) != 1) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (gb_sweep* s : ctx->sweep_cache) sweep_free(s);
-  ctx->sweep_cache.clear();
   for (gb_pool_block& b : ctx->pool) { if (b.d) cudaFree(b.d); if (b.h) cudaFreeHost(b.h); }
   ctx->pool.clear();
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+extern "C" gb_status gb_ctx_destroy(gb_ctx* ctx) {
+  if (!ctx) return GB_OK;
+  {
+    GB_LOCK(ctx);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    std::vector<gb_sweep*> cache;
+    cache.swap(ctx->sweep_cache);
+    for (gb_sweep* s : cache) sweep_free(s);
+  }
+  ctx_release(ctx);
   return GB_OK;
 }
 extern "C" gb_status gb_ctx_synchronize(gb_ctx* ctx) {
@@ -146,7 +163,7 @@ extern "C" gb_status gb_cloud_upload(gb_ctx* ctx, size_t n, const double* xyzw, 
   GB_CUDA(cudaSetDevice(ctx->device));
   gb_cloud* c = new (std::nothrow) gb_cloud();
   if (!c) return GB_ERR_INTERNAL;
-  c->ctx = ctx; c->n = n; c->base = nullptr; c->bytes = 0;
+  c->device = ctx->device; c->n = n; c->base = nullptr; c->bytes = 0;
   c->p0 = nullptr; c->p1 = nullptr; c->p2 = nullptr; c->normals = nullptr; c->perm = nullptr; c->inv_perm = nullptr;
   if (n == 0) { *out = c; return GB_OK; }
   // the reference casts Vector4d / Matrix4d to float on the host before the copy; so do we,
@@ -212,7 +229,7 @@ extern "C" gb_status gb_cloud_download(const gb_cloud* c, float* xyz, float* cov
   if (c->n == 0) return GB_OK;
   std::vector<float4> h0(c->n), h1(c->n);
   std::vector<float> h2(c->n);
-  GB_CUDA(cudaStreamSynchronize(c->ctx->stream));
+  GB_CUDA(cudaSetDevice(c->device));  // the upload returned after its stream had drained: plain synchronous copies are safe
   GB_CUDA(cudaMemcpy(h0.data(), c->p0, sizeof(float4) * c->n, cudaMemcpyDeviceToHost));
   GB_CUDA(cudaMemcpy(h1.data(), c->p1, sizeof(float4) * c->n, cudaMemcpyDeviceToHost));
   GB_CUDA(cudaMemcpy(h2.data(), c->p2, sizeof(float) * c->n, cudaMemcpyDeviceToHost));
@@ -225,11 +242,18 @@ extern "C" gb_status gb_cloud_download(const gb_cloud* c, float* xyz, float* cov
   }
   return GB_OK;
 }
+extern "C" gb_status gb_cloud_device_ptrs(const gb_cloud* c, void** p0, void** p1, void** p2, void** normals) {
+  GB_REQUIRE(c, "null cloud");
+  if (p0) *p0 = c->p0;
+  if (p1) *p1 = c->p1;
+  if (p2) *p2 = c->p2;
+  if (normals) *normals = c->normals;
+  return GB_OK;
+}
 extern "C" gb_status gb_cloud_destroy(gb_cloud* c) {
   if (!c) return GB_OK;
-  cudaSetDevice(c->ctx->device);
-  cudaStreamSynchronize(c->ctx->stream);
-  if (c->base) cudaFree(c->base);
+  cudaSetDevice(c->device);
+  if (c->base) cudaFree(c->base);  // cudaFree synchronises with every stream that may still read the cloud
   delete c;
   return GB_OK;
 }
@@ -265,7 +289,7 @@ extern "C" gb_status gb_voxelmap_info(const gb_voxelmap* m, int* num_voxels, int
 }
 extern "C" gb_status gb_voxelmap_download(const gb_voxelmap* m, int32_t* buckets, int32_t* num_points, float* means, float* cov6) {
   GB_REQUIRE(m, "null map");
-  GB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  GB_CUDA(cudaSetDevice(m->device));
   if (buckets) GB_CUDA(cudaMemcpy(buckets, m->buckets, sizeof(int4) * (size_t)m->num_buckets, cudaMemcpyDeviceToHost));
   if ((num_points || means || cov6) && m->num_voxels > 0) {
     std::vector<float4> h(3 * (size_t)m->num_voxels);
@@ -281,8 +305,7 @@ extern "C" gb_status gb_voxelmap_download(const gb_voxelmap* m, int32_t* buckets
 }
 extern "C" gb_status gb_voxelmap_destroy(gb_voxelmap* m) {
   if (!m) return GB_OK;
-  cudaSetDevice(m->ctx->device);
-  cudaStreamSynchronize(m->ctx->stream);
+  cudaSetDevice(m->device);
   if (m->base) cudaFree(m->base);
   if (m->buckets) cudaFree(m->buckets);
   delete m;
@@ -292,18 +315,15 @@ extern "C" gb_status gb_voxelmap_destroy(gb_voxelmap* m) {
 // ---------------------------------------------------------------------------------------------
 // factors and sweeps
 // ---------------------------------------------------------------------------------------------
-// Cross links factor <-> sweep (a factor may sit in cached sweeps of several contexts): guarded by one registry mutex.
-static std::mutex g_registry_mu;
-static std::atomic<uint64_t> g_next_factor_id{1};
-
 extern "C" gb_status gb_vgicp_factor_create(gb_ctx* ctx, const gb_voxelmap* target, const gb_cloud* source, int flags, gb_factor** out) {
   GB_REQUIRE(ctx && target && source && out, "null argument");
   // clouds / voxel maps may have been uploaded through another context (another module thread): device memory is shared,
   // and every producer call returns only after its stream has drained, so only the DEVICE has to match
-  GB_REQUIRE(target->ctx->device == ctx->device && source->ctx->device == ctx->device, "cloud / voxel map live on another device");
+  GB_REQUIRE(target->device == ctx->device && source->device == ctx->device, "cloud / voxel map live on another device");
   gb_factor* f = new (std::nothrow) gb_factor();
   if (!f) return GB_ERR_INTERNAL;
   f->ctx = ctx; f->target = target; f->source = source; f->flags = flags; f->single = nullptr; f->id = g_next_factor_id.fetch_add(1);
+  ctx_retain(ctx);
   *out = f;
   return GB_OK;
 }
@@ -335,21 +355,24 @@ static bool pool_get(gb_ctx* ctx, size_t d_need, size_t h_need, gb_pool_block* o
 static void sweep_free(gb_sweep* s) {
   if (!s) return;
   gb_ctx* ctx = s->ctx;
-  GB_LOCK(ctx);
-  cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
   {
-    std::lock_guard<std::mutex> reg(g_registry_mu);
-    for (gb_factor* f : s->factors) {
-      if (!f) continue;  // already destroyed (the sweep is stale)
-      auto it = std::find(f->users.begin(), f->users.end(), s);
-      if (it != f->users.end()) f->users.erase(it);
+    GB_LOCK(ctx);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    {
+      std::lock_guard<std::mutex> reg(g_registry_mu);
+      for (gb_factor* f : s->factors) {
+        if (!f) continue;  // already destroyed (the sweep is stale)
+        auto it = std::find(f->users.begin(), f->users.end(), s);
+        if (it != f->users.end()) f->users.erase(it);
+      }
     }
+    for (int k = 0; k < 2; k++) if (s->pose_ev[k]) cudaEventDestroy(s->pose_ev[k]);
+    if (s->d_pair_ptr) cudaFree(s->d_pair_ptr);
+    pool_put(ctx, s->pool_d, s->pool_d_cap, s->pool_h, s->pool_h_cap);
+    delete s;
   }
-  for (int k = 0; k < 2; k++) if (s->pose_ev[k]) cudaEventDestroy(s->pose_ev[k]);
-  if (s->d_pair_ptr) cudaFree(s->d_pair_ptr);
-  pool_put(ctx, s->pool_d, s->pool_d_cap, s->pool_h, s->pool_h_cap);
-  delete s;
+  ctx_release(ctx);
 }
 
 extern "C" gb_status gb_vgicp_factor_destroy(gb_factor* f) {
@@ -365,7 +388,9 @@ extern "C" gb_status gb_vgicp_factor_destroy(gb_factor* f) {
     }
     f->users.clear();
   }
+  gb_ctx* ctx = f->ctx;
   delete f;
+  ctx_release(ctx);
   return GB_OK;
 }
 
@@ -382,13 +407,14 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   uint64_t total_pts = 0;
   for (size_t f = 0; f < F; f++) {
     GB_REQUIRE(factors[f], "null factor");
-    GB_REQUIRE(factors[f]->source->ctx->device == ctx->device && factors[f]->target->ctx->device == ctx->device, "factor lives on another device");
+    GB_REQUIRE(factors[f]->source->device == ctx->device && factors[f]->target->device == ctx->device, "factor lives on another device");
     total_pts += factors[f]->source->n;
   }
   GB_LOCK(ctx);
   GB_CUDA(cudaSetDevice(ctx->device));
   gb_sweep* s = new (std::nothrow) gb_sweep();
   if (!s) return GB_ERR_INTERNAL;
+  ctx_retain(ctx);
   s->ctx = ctx; s->F = F; s->factors.assign(factors, factors + F);
   s->d_descs = nullptr; s->d_tiles = nullptr; s->d_poses = nullptr; s->d_poses_eval = nullptr; s->d_accum = nullptr; s->d_done = nullptr; s->d_out = nullptr;
   s->h_poses_eval = nullptr; s->h_out = nullptr; s->d_slab = nullptr; s->num_pairs = 0;
@@ -399,7 +425,7 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   s->pool_d = nullptr; s->pool_d_cap = 0; s->pool_h = nullptr; s->pool_h_cap = 0;
 
   // kernel generation and work-item size
-  s->kernel_version = env_int("GB_KERNEL", 4) == 3 ? 3 : 4;
+  { const int kv = env_int("GB_KERNEL", 4); s->kernel_version = (kv == 3 || kv == 5) ? kv : 4; }
   s->stage_points = env_int("GB_STAGE", 128) == 64 ? 64 : 128;
   const int T = s->kernel_version == 4 ? s->stage_points : 32;
   const int ctas_per_sm = (s->kernel_version == 4 && s->stage_points == 64) ? 3 : 2;
@@ -459,10 +485,10 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     gb_pool_block blk{nullptr, 0, nullptr, 0};
     if (!pool_get(ctx, total, h_total, &blk)) {
       cudaError_t e = cudaMalloc(&blk.d, total);
-      if (e != cudaSuccess) { delete s; gb_set_error("cudaMalloc(%zu): %s", total, cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
+      if (e != cudaSuccess) { delete s; ctx_release(ctx); gb_set_error("cudaMalloc(%zu): %s", total, cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
       blk.d_cap = total;
       e = cudaMallocHost(&blk.h, h_total);
-      if (e != cudaSuccess) { cudaFree(blk.d); delete s; gb_set_error("cudaMallocHost: %s", cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
+      if (e != cudaSuccess) { cudaFree(blk.d); delete s; ctx_release(ctx); gb_set_error("cudaMallocHost: %s", cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
       blk.h_cap = h_total;
     }
     s->pool_d = blk.d; s->pool_d_cap = blk.d_cap; s->pool_h = blk.h; s->pool_h_cap = blk.h_cap;
@@ -642,6 +668,40 @@ extern "C" gb_status gb_vgicp_error(gb_factor* f, const double T_lin[16], const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// solver hand-off: gtsam::HessianFactor blocks (global_mapping.cpp:492-501)
+// ---------------------------------------------------------------------------------------------
+extern "C" gb_status gb_hessian_blocks(const gb_linearized6* L, double error_scale, double* G11, double* G12, double* g1, double* G22, double* g2, double* f) {
+  GB_REQUIRE(L, "null record");
+  if (G11) memcpy(G11, L->H_tt, sizeof(double) * 36);
+  if (G12) memcpy(G12, L->H_ts, sizeof(double) * 36);
+  if (G22) memcpy(G22, L->H_ss, sizeof(double) * 36);
+  for (int k = 0; k < 6; k++) {
+    if (g1) g1[k] = -L->b_t[k];  // HessianFactor takes the NEGATED gradients
+    if (g2) g2[k] = -L->b_s[k];
+  }
+  if (f) *f = error_scale * L->error;
+  return GB_OK;
+}
+extern "C" gb_status gb_slab_row_hessian_blocks(const float* row, double error_scale, double* G11, double* G12, double* g1, double* G22, double* g2, double* f, double* num_inliers) {
+  GB_REQUIRE(row, "null slab row");
+  // row: H_tt upper (21, row-major i <= j) | H_ts (36, column-major) | H_ss upper (21) | b_t (6) | b_s (6) | error | num_inliers
+  int u = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = i; j < 6; j++, u++) {
+      if (G11) { G11[j * 6 + i] = row[u]; G11[i * 6 + j] = row[u]; }
+      if (G22) { G22[j * 6 + i] = row[57 + u]; G22[i * 6 + j] = row[57 + u]; }
+    }
+  if (G12) for (int e = 0; e < 36; e++) G12[e] = row[21 + e];
+  for (int k = 0; k < 6; k++) {
+    if (g1) g1[k] = -(double)row[78 + k];
+    if (g2) g2[k] = -(double)row[84 + k];
+  }
+  if (f) *f = error_scale * (double)row[90];
+  if (num_inliers) *num_inliers = (double)row[91];
+  return GB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // fused multi-GPU result exchange (peer slabs over CUDA IPC)
 // ---------------------------------------------------------------------------------------------
 static size_t peer_alloc_bytes(size_t num_pairs, int world) {
@@ -671,6 +731,7 @@ extern "C" gb_status gb_peer_slab_create(gb_ctx* ctx, size_t num_pairs, int worl
   ps->h_pinned = nullptr;
   e = cudaMallocHost((void**)&ps->h_pinned, num_pairs * GB_SLAB_STRIDE * sizeof(float) + 64);
   if (e != cudaSuccess) { cudaFree(ps->local); delete ps; gb_set_error("cudaMallocHost: %s", cudaGetErrorString(e)); return GB_ERR_OUT_OF_MEMORY; }
+  ctx_retain(ctx);
   *out = ps;
   return GB_OK;
 }
@@ -708,7 +769,9 @@ extern "C" gb_status gb_peer_slab_destroy(gb_peer_slab* ps) {
     if (ps->opened[p]) cudaIpcCloseMemHandle(ps->peer[p]);
   if (ps->local) cudaFree(ps->local);
   if (ps->h_pinned) cudaFreeHost(ps->h_pinned);
+  gb_ctx* ctx = ps->ctx;
   delete ps;
+  ctx_release(ctx);
   return GB_OK;
 }
 

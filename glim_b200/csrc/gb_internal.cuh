@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -42,7 +43,7 @@ void gb_set_error(const char* fmt, ...);
 // Voxel map: open-addressing table of 16-byte buckets {cx, cy, cz, voxel index (-1 = empty)} and
 // 48-byte voxel records (3 x float4): {mx, my, mz, c00} {c01, c02, c11, c12} {c22, num_points, 0, 0}.
 struct gb_cloud {
-  gb_ctx* ctx;
+  int device;       // clouds / voxel maps do NOT keep their creating context: they outlive it when frames migrate between threads
   size_t n;
   float4* p0;
   float4* p1;
@@ -57,7 +58,7 @@ struct gb_cloud {
 };
 
 struct gb_voxelmap {
-  gb_ctx* ctx;
+  int device;
   float resolution, inv_res;
   int max_scan;
   int num_voxels, num_buckets;
@@ -174,6 +175,7 @@ struct gb_ctx {
   void* pinned;
   size_t pinned_cap;
   uint64_t launches;
+  std::atomic<int> refs;   // owner + live factors / sweeps / peer slabs; the context is torn down when the last one lets go
   std::vector<gb_sweep*> sweep_cache;
   std::vector<gb_pool_block> pool;  // device + pinned blocks of retired sweeps, reused by the next gb_sweep_create
   // A context may be driven from more than one host thread (a frame cloned by the odometry thread is later used by the

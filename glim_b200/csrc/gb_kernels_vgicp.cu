@@ -429,18 +429,28 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep4(
     nxt = __shfl_sync(0xffffffffu, nxt, 0);
   }
 
-  auto desc_of = [&](int f) -> const FactorDesc* { return cached ? &cache->desc[f] : &descs[f]; };
+  // Descriptor reads keep their address space (LDS from the cache or LDG from the table): a merged generic pointer made the
+  // compiler re-load D.mask / D.inv_res with generic LD.E inside the stage loop (26 % of the stall samples of the first version).
+  auto desc_of = [&](int f) -> FactorDesc { FactorDesc d; if (cached) d = cache->desc[f]; else d = descs[f]; return d; };
+  auto tiles_of = [&](int f) -> int { return cached ? cache->desc[f].num_tiles : descs[f].num_tiles; };
+  // lane 0: start the copy of `cnt` points of factor f's source cloud
+  auto issue_factor_stage = [&](int f, int b, int first, int cnt) {
+    const float4 *p0, *p1;
+    const float* p2;
+    if (cached) { p0 = cache->desc[f].p0; p1 = cache->desc[f].p1; p2 = cache->desc[f].p2; } else { p0 = descs[f].p0; p1 = descs[f].p1; p2 = descs[f].p2; }
+    issue_stage<T>(&ws.buf[b], b ? bar1 : bar0, p0, p1, p2, first, cnt);
+  };
   // lane 0: start the copy of the first stage of item `it_idx` into buffer `b` (the item itself is re-read at its start)
   auto prefetch_item = [&](int it_idx, int b) {
     const int2 it = __ldg(&items[it_idx]);
-    const FactorDesc* dp = desc_of(it.x);
-    const int cnt = min(min(chunk, dp->n - it.y), T);
-    if (cnt > 0) issue_stage<T>(&ws.buf[b], b ? bar1 : bar0, dp->p0, dp->p1, dp->p2, it.y, cnt);
+    const int n = cached ? cache->desc[it.x].n : descs[it.x].n;
+    const int cnt = min(min(chunk, n - it.y), T);
+    if (cnt > 0) issue_factor_stage(it.x, b, it.y, cnt);
   };
   // lane 0 (after a __syncwarp): publish the ticket of the previous item's factor; is that factor complete now?
   auto publish = [&](int pf) -> int {
     const unsigned t = ticket_release(&done[pf]);
-    const int last = (t == (unsigned)desc_of(pf)->num_tiles - 1u);
+    const int last = (t == (unsigned)tiles_of(pf) - 1u);
     if (last) done[pf] = 0u;  // self-cleaning: nobody draws this ticket again in this launch
     return last;
   };
@@ -456,15 +466,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep4(
     if (dynamic && lane == 0) nxt2 = (int)(atomicAdd(item_ctr, 1ull) - ctr_base) + total_warps;  // consumed at the end of the item
     const int2 it = __ldg(&items[item]);
     const int f = it.x;
-    const FactorDesc* const dp = desc_of(f);
     // only what the lookup / derivative phases need stays in registers; the plane pointers are re-read by lane 0 when it
     // issues a copy
-    FactorDesc D;
-    D.buckets = dp->buckets; D.voxels = dp->voxels; D.mask = dp->mask; D.max_scan = dp->max_scan; D.inv_res = dp->inv_res;
-    const PoseF P = cached ? cache->pose[f] : pose_from_colmajor(poses + (size_t)f * 16);
+    const FactorDesc D = desc_of(f);
+    PoseF P;
+    if (cached) P = cache->pose[f]; else P = pose_from_colmajor(poses + (size_t)f * 16);
     PoseF Pe = P;
-    if (MODE == GB_MODE_ERROR) Pe = cached ? cache->pose_eval[f] : pose_from_colmajor(poses_eval + (size_t)f * 16);
-    const int item_end = min(it.y + chunk, dp->n);
+    if (MODE == GB_MODE_ERROR) { if (cached) Pe = cache->pose_eval[f]; else Pe = pose_from_colmajor(poses_eval + (size_t)f * 16); }
+    const int item_end = min(it.y + chunk, D.n);
     const int nstages = (max(0, item_end - it.y) + T - 1) / T;  // 0: factor without points (its epilogue still runs)
 
     float acc[32];
@@ -480,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep4(
       const bool last_stage = (s == nstages - 1);
       // ---- keep the copy engine one stage ahead ----
       if (lane == 0) {
-        if (!last_stage) issue_stage<T>(&ws.buf[cur ^ 1], (cur ^ 1) ? bar1 : bar0, dp->p0, dp->p1, dp->p2, wb + T, min(T, item_end - wb - T));
+        if (!last_stage) issue_factor_stage(f, cur ^ 1, wb + T, min(T, item_end - wb - T));
         else if (nxt < num_items) prefetch_item(nxt, cur ^ 1);
       }
       StageBuf<T>& sb = ws.buf[cur];
@@ -529,14 +538,29 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep4(
       __syncwarp();
 
       // ---------------- phase B: derivative pass over full groups of 32 hits ----------------
+      // software pipelined: the voxel record of the lane's NEXT hit is in flight while the current one is processed
       const int nproc = last_stage ? nq : (nq & ~31);
+      {
+        int k = lane;
+        uint2 e = make_uint2(0u, 0u);
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
+        if (k < nproc) {
+          e = q[k];
+          v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]); v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]); v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
+        }
 #pragma unroll 1
-      for (int k = lane; k < nproc; k += 32) {
-        const uint2 e = q[k];
-        const float4 v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]);
-        const float4 v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]);
-        const float4 v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
-        accumulate_hit<MODE>(acc, Pe, sb.p0[e.x], sb.p1[e.x], sb.p2[e.x], v0, v1, v2);
+        while (k < nproc) {
+          const int kn = k + 32;
+          uint2 en = e;
+          float4 n0 = v0, n1 = v1, n2 = v2;
+          if (kn < nproc) {
+            en = q[kn];
+            n0 = __ldg(&D.voxels[3 * (size_t)en.y + 0]); n1 = __ldg(&D.voxels[3 * (size_t)en.y + 1]); n2 = __ldg(&D.voxels[3 * (size_t)en.y + 2]);
+          }
+          accumulate_hit<MODE>(acc, Pe, sb.p0[e.x], sb.p1[e.x], sb.p2[e.x], v0, v1, v2);
+          e = en; v0 = n0; v1 = n1; v2 = n2;
+          k = kn;
+        }
       }
       // ---------------- carry the partial group over to the next stage ----------------
       if (!last_stage) {
@@ -580,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep4(
     // scratch: the stage buffer that was consumed last (the other one may be receiving the next item's first stage)
     if (pend_f >= 0 && __shfl_sync(0xffffffffu, pend_last, 0)) {
       fence_acquire();
-      const FactorDesc Dp = *desc_of(pend_f);
+      const FactorDesc Dp = desc_of(pend_f);
       double* scratch = reinterpret_cast<double*>(&ws.buf[cur ^ 1]);
       factor_epilogue(pend_f, Dp, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, acc_slots, out, slab, scratch);
       if (PEER && MODE == GB_MODE_LINEARIZE) pair_push(Dp, out, peer, reinterpret_cast<float*>(scratch + kEpilogueDoubles));
@@ -600,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep4(
   if (lane == 0) pend_last = publish(pend_f);
   if (__shfl_sync(0xffffffffu, pend_last, 0)) {
     fence_acquire();
-    const FactorDesc Dp = *desc_of(pend_f);
+    const FactorDesc Dp = desc_of(pend_f);
     double* scratch = reinterpret_cast<double*>(&ws.buf[cur ^ 1]);
     factor_epilogue(pend_f, Dp, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, acc_slots, out, slab, scratch);
     if (PEER && MODE == GB_MODE_LINEARIZE) pair_push(Dp, out, peer, reinterpret_cast<float*>(scratch + kEpilogueDoubles));
@@ -720,6 +744,177 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep3(
   }
 }
 
+// =============================================================================================
+// k_vgicp_sweep5 -- register-staged like v3 (no large shared-memory carve-out, L1 stays big), with the per-item latency
+// chain cut: descriptor / pose cache in shared memory for small factor sets, one-item look-ahead of the work queue,
+// software-pipelined lookup (the next group's points are loaded while the current group's buckets are in flight),
+// lazily published release tickets (no __threadfence, no L1 flush per item).  GB_KERNEL=5.
+// =============================================================================================
+template <int MODE, bool PEER>
+__global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep5(
+  const FactorDesc* __restrict__ descs, int num_factors, const double* __restrict__ poses, const double* __restrict__ poses_eval,
+  const int2* __restrict__ items, int num_items, int chunk,
+  unsigned long long* __restrict__ item_ctr, unsigned long long ctr_base,
+  double* __restrict__ accum, int acc_slots, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab, const PeerPush* __restrict__ peer) {
+  __shared__ __align__(16) uint2 s_q[kWarps][kSubMax];
+  __shared__ CtaCache cache_s;
+  CtaCache* const cache = &cache_s;
+  constexpr int U = kLookupUnroll;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  uint2* __restrict__ q = s_q[warp];
+
+  const bool cached = num_factors <= kDescCache;
+  if (cached) {
+    for (int f = threadIdx.x; f < num_factors; f += kThreads) {
+      cache->desc[f] = descs[f];
+      cache->pose[f] = pose_from_colmajor(poses + (size_t)f * 16);
+      if (MODE == GB_MODE_ERROR) cache->pose_eval[f] = pose_from_colmajor(poses_eval + (size_t)f * 16);
+    }
+    __syncthreads();  // the only block-level barrier of the kernel
+  }
+  auto desc_of = [&](int f) -> FactorDesc { FactorDesc d; if (cached) d = cache->desc[f]; else d = descs[f]; return d; };
+  auto publish = [&](int pf) -> int {  // lane 0, after a __syncwarp
+    const unsigned t = ticket_release(&done[pf]);
+    const int last = (t == (unsigned)(cached ? cache->desc[pf].num_tiles : descs[pf].num_tiles) - 1u);
+    if (last) done[pf] = 0u;
+    return last;
+  };
+
+  const int total_warps = gridDim.x * kWarps;
+  const bool dynamic = num_items > total_warps;
+  int item = blockIdx.x * kWarps + warp;  // first item: static
+  if (item >= num_items) return;
+  int nxt = 0x7fffffff;  // one-item look-ahead of the queue
+  if (dynamic) {
+    if (lane == 0) nxt = (int)(atomicAdd(item_ctr, 1ull) - ctr_base) + total_warps;
+    nxt = __shfl_sync(0xffffffffu, nxt, 0);
+  }
+  int2 it = __ldg(&items[item]);
+  int pend_f = -1, pend_last = 0;
+
+  while (true) {
+    int nxt2 = 0x7fffffff;
+    if (dynamic && lane == 0) nxt2 = (int)(atomicAdd(item_ctr, 1ull) - ctr_base) + total_warps;
+    int2 it_next = make_int2(0, 0);
+    if (nxt < num_items) it_next = __ldg(&items[nxt]);  // the next item's identity travels while this item is processed
+    const int f = it.x;
+    const FactorDesc D = desc_of(f);
+    PoseF P;
+    if (cached) P = cache->pose[f]; else P = pose_from_colmajor(poses + (size_t)f * 16);
+    PoseF Pe = P;
+    if (MODE == GB_MODE_ERROR) { if (cached) Pe = cache->pose_eval[f]; else Pe = pose_from_colmajor(poses_eval + (size_t)f * 16); }
+    const int item_end = min(it.y + chunk, D.n);
+
+    float acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) acc[k] = 0.f;
+    bool published = (pend_f < 0);
+
+    for (int wb = it.y; wb < item_end; wb += kSubMax) {
+      const int we = min(wb + kSubMax, item_end);
+      int nq = 0;  // warp-uniform queue length
+      // ---------------- phase A, software pipelined: group g's buckets and group g+1's points are in flight together ----
+      float ax[U], ay[U], az[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const float4 a0 = __ldg(&D.p0[min(wb + u * 32 + lane, we - 1)]);
+        ax[u] = a0.x; ay[u] = a0.y; az[u] = a0.z;
+      }
+      for (int i0 = wb; i0 < we; i0 += 32 * U) {
+        int cx[U], cy[U], cz[U];
+        uint32_t h[U];
+        int4 b[U], b1[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          float qx, qy, qz;
+          transform(P, ax[u], ay[u], az[u], qx, qy, qz);
+          cx[u] = gb_coord(qx, D.inv_res); cy[u] = gb_coord(qy, D.inv_res); cz[u] = gb_coord(qz, D.inv_res);
+          const float sum = (qx + qy) + qz;
+          if (!(sum == sum)) cx[u] = 0x7fffffff;  // NaN point: a coordinate no voxel has
+          h[u] = gb_hash(cx[u], cy[u], cz[u]);
+          b[u] = __ldg(&D.buckets[h[u] & D.mask]);
+          b1[u] = __ldg(&D.buckets[(h[u] + 1u) & D.mask]);
+        }
+        if (i0 + 32 * U < we) {
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const float4 a0 = __ldg(&D.p0[min(i0 + 32 * U + u * 32 + lane, we - 1)]);
+            ax[u] = a0.x; ay[u] = a0.y; az[u] = a0.z;
+          }
+        }
+        if (!published) {  // the previous item's ticket: the MEMBAR of the release overlaps with the loads above
+          published = true;
+          __syncwarp();
+          if (lane == 0) pend_last = publish(pend_f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int i = i0 + u * 32 + lane;
+          int v = resolve_probe(D, b[u], b1[u], h[u], cx[u], cy[u], cz[u]);
+          if (i >= we) v = -1;
+          const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
+          if (v >= 0) q[nq + __popc(m & lt_mask)] = make_uint2((unsigned)i, (unsigned)v);
+          nq += __popc(m);
+        }
+      }
+      __syncwarp();
+      // ---------------- phase B ----------------
+#pragma unroll 2
+      for (int k = lane; k < nq; k += 32) {
+        const uint2 e = q[k];
+        const int i = (int)e.x;
+        const float4 a0 = __ldg(&D.p0[i]);
+        const float4 a1 = __ldg(&D.p1[i]);
+        const float a2 = __ldg(&D.p2[i]);
+        const float4 v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]);
+        const float4 v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]);
+        const float4 v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
+        accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
+      }
+      __syncwarp();  // the queue is overwritten by the next round
+    }
+    if (!published) {  // empty factor
+      __syncwarp();
+      if (lane == 0) pend_last = publish(pend_f);
+    }
+
+    double* __restrict__ my_acc = accum + ((size_t)f * acc_slots + (size_t)(item & (acc_slots - 1))) * GB_ACC_STRIDE;
+    if (MODE == GB_MODE_LINEARIZE) {
+      const float r = warp_reduce_scatter32(acc, lane);
+      if (lane < 29) atomicAdd(&my_acc[lane], (double)r);
+    } else {
+      float e = acc[27], n = acc[28];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) { e += __shfl_xor_sync(0xffffffffu, e, o); n += __shfl_xor_sync(0xffffffffu, n, o); }
+      if (lane == 27) atomicAdd(&my_acc[27], (double)e);
+      if (lane == 28) atomicAdd(&my_acc[28], (double)n);
+    }
+    // epilogue of the PREVIOUS item's factor, if that item was its last
+    if (pend_f >= 0 && __shfl_sync(0xffffffffu, pend_last, 0)) {
+      fence_acquire();
+      const FactorDesc Dp = desc_of(pend_f);
+      factor_epilogue(pend_f, Dp, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, acc_slots, out, slab, reinterpret_cast<double*>(q));
+      if (PEER && MODE == GB_MODE_LINEARIZE) pair_push(Dp, out, peer, reinterpret_cast<float*>(q) + 2 * kEpilogueDoubles);
+      __syncwarp();
+    }
+    pend_f = f;
+    pend_last = 0;
+    item = nxt;
+    it = it_next;
+    nxt = __shfl_sync(0xffffffffu, nxt2, 0);
+    if (item >= num_items) break;
+  }
+  __syncwarp();
+  if (lane == 0) pend_last = publish(pend_f);
+  if (__shfl_sync(0xffffffffu, pend_last, 0)) {
+    fence_acquire();
+    const FactorDesc Dp = desc_of(pend_f);
+    factor_epilogue(pend_f, Dp, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, acc_slots, out, slab, reinterpret_cast<double*>(q));
+    if (PEER && MODE == GB_MODE_LINEARIZE) pair_push(Dp, out, peer, reinterpret_cast<float*>(q) + 2 * kEpilogueDoubles);
+  }
+}
+
 // overlap: one thread per source point, count points that hit an occupied voxel of any target
 __global__ void __launch_bounds__(256) k_overlap(int num_targets, const FactorDesc* __restrict__ descs, const double* __restrict__ poses, int n, int* __restrict__ count) {
   extern __shared__ float s_poses[];  // num_targets x 12
@@ -775,6 +970,12 @@ static cudaError_t launch4(gb_sweep* s, const double* poses_eval, float* slab, c
 }
 
 template <int MODE, bool PEER>
+static cudaError_t launch5(gb_sweep* s, const double* poses_eval, float* slab, const PeerPush* pp) {
+  k_vgicp_sweep5<MODE, PEER><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, (int)s->F, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
+  return cudaGetLastError();
+}
+
+template <int MODE, bool PEER>
 static cudaError_t launch3(gb_sweep* s, const double* poses_eval, float* slab, const PeerPush* pp) {
   k_vgicp_sweep3<MODE, PEER><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
   return cudaGetLastError();
@@ -811,6 +1012,9 @@ gb_status gb_launch_sweep(gb_sweep* s, int mode) {
   if (s->kernel_version == 3) {
     if (mode == GB_MODE_LINEARIZE) e = peer ? launch3<GB_MODE_LINEARIZE, true>(s, pe, slab, pp) : launch3<GB_MODE_LINEARIZE, false>(s, pe, slab, pp);
     else e = launch3<GB_MODE_ERROR, false>(s, pe, slab, pp);
+  } else if (s->kernel_version == 5) {
+    if (mode == GB_MODE_LINEARIZE) e = peer ? launch5<GB_MODE_LINEARIZE, true>(s, pe, slab, pp) : launch5<GB_MODE_LINEARIZE, false>(s, pe, slab, pp);
+    else e = launch5<GB_MODE_ERROR, false>(s, pe, slab, pp);
   } else if (s->stage_points == 64) {
     if (mode == GB_MODE_LINEARIZE) e = peer ? launch4<GB_MODE_LINEARIZE, 64, true, 3>(s, pe, slab, pp) : launch4<GB_MODE_LINEARIZE, 64, false, 3>(s, pe, slab, pp);
     else e = launch4<GB_MODE_ERROR, 64, false, 3>(s, pe, slab, pp);

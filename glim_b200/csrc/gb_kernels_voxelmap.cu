@@ -134,7 +134,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 gb_status gb_voxelmap_build_impl(gb_ctx* ctx, const gb_cloud* cloud, float resolution, int init_buckets, int max_scan, double drop_rate, gb_voxelmap* m) {
   const int n = (int)cloud->n;
   cudaStream_t st = ctx->stream;
-  m->ctx = ctx;
+  m->device = ctx->device;
   m->resolution = resolution;
   m->inv_res = 1.0f / resolution;
   m->max_scan = max_scan;

@@ -13,9 +13,13 @@
  *     A gb_factor BORROWS its cloud and voxel map (the C++ shim keeps shared_ptrs alive, as the
  *     reference factor does); destroying a cloud or map that a live factor uses is a caller bug.
  *     Likewise a gb_sweep BORROWS its factors, and a sweep with a peer slab attached borrows the slab.
- *   - one gb_ctx per host thread / GPU (the reference drives each module from exactly one
- *     executor thread: src/glim/odometry/async_odometry_estimation.cpp:15).  A ctx owns one CUDA
- *     stream; all work of its handles is ordered on that stream.
+ *   - a gb_ctx owns one CUDA stream; all work issued through it is ordered on that stream.  The natural
+ *     use is one gb_ctx per module thread (the reference drives each module from exactly one executor
+ *     thread: src/glim/odometry/async_odometry_estimation.cpp:15), but a ctx may be called from several
+ *     host threads (every entry point takes the ctx's mutex), and clouds / voxel maps uploaded through
+ *     one ctx may be used by factors and sweeps of another ctx of the same device: frames migrate from
+ *     the odometry thread to sub-mapping to global mapping (async_sub_mapping.cpp:8,
+ *     async_global_mapping.cpp:24).  Every upload / build call returns after its stream has drained.
  *   - 4x4 poses are 16 doubles, COLUMN-MAJOR (Eigen::Isometry3d::data()).
  *   - 6x6 blocks are column-major, tangent order [rotation(3); translation(3)] (gtsam::Pose3).
  *   - there is NO CPU fallback: without a CUDA device every call fails with GB_ERR_NO_DEVICE.
@@ -47,6 +51,7 @@ typedef struct gb_cloud gb_cloud;       /* gtsam_points::PointCloudGPU          
 typedef struct gb_voxelmap gb_voxelmap; /* gtsam_points::GaussianVoxelMapGPU                                        */
 typedef struct gb_factor gb_factor;     /* gtsam_points::IntegratedVGICPFactorGPU                                   */
 typedef struct gb_sweep gb_sweep;       /* gtsam_points::NonlinearFactorSetGPU (a prepared batch of factors)        */
+#define GB_SLAB_STRIDE 96               /* floats per row of the per-pair Hessian slab (layout below, at gb_sweep_create) */
 
 /* LinearizedSystem6 of the reference GPU factor, widened to fp64.
  * To GTSAM: HessianFactor(k_t, k_s, H_tt, H_ts, -b_t, H_ss, -b_s, error); unary: (k_s, H_ss, -b_s, error).
@@ -92,6 +97,10 @@ GB_API gb_status gb_cloud_upload(gb_ctx* ctx, size_t n, const double* xyzw, cons
 GB_API gb_status gb_cloud_size(const gb_cloud* cloud, size_t* n);
 /* device -> host copy of the fp32 device data: xyz N x 3, cov6 N x 6 (c00 c01 c02 c11 c12 c22); either may be NULL */
 GB_API gb_status gb_cloud_download(const gb_cloud* cloud, float* xyz, float* cov6);
+/* device pointers of the planes (points_gpu / covs_gpu / normals_gpu of the reference's PointCloud: GLIM only tests them for
+ * null, sub_mapping.cpp:165, global_mapping.cpp:252, :330).  p0 = N x float4 {x y z c00}, p1 = N x float4 {c01 c02 c11 c12},
+ * p2 = N x float c22, normals = N x float4 or NULL; stored in the cloud's internal (Morton) order.  Any output may be NULL. */
+GB_API gb_status gb_cloud_device_ptrs(const gb_cloud* cloud, void** p0, void** p1, void** p2, void** normals);
 GB_API gb_status gb_cloud_destroy(gb_cloud* cloud);
 
 /* ---- GaussianVoxelMapGPU(resolution, init_num_buckets = 8192*2, max_bucket_scan_count = 10,
@@ -123,6 +132,13 @@ GB_API gb_status gb_vgicp_error(gb_factor* factor, const double T_lin[16], const
 GB_API gb_status gb_factor_set_linearize(gb_ctx* ctx, size_t num_factors, gb_factor* const* factors, const double* T_target_source /* F x 16 */, gb_linearized6* out /* F */);
 GB_API gb_status gb_factor_set_error(gb_ctx* ctx, size_t num_factors, gb_factor* const* factors, const double* T_lin /* F x 16 */, const double* T_eval /* F x 16 */, double* errors /* F */);
 
+/* ---- Solver hand-off (global_mapping.cpp:492-501 feeds these to isam2->update): the blocks of
+ *      gtsam::HessianFactor(k_t, k_s, G11 = H_tt, G12 = H_ts, g1 = -b_t, G22 = H_ss, g2 = -b_s, f = error_scale * error),
+ *      6x6 blocks column-major, from one factor record or from one fp32 row of the pair slab (levels pre-summed on the
+ *      device).  Host-only helpers (no device needed); for a unary factor use G22 / g2 / f. ---- */
+GB_API gb_status gb_hessian_blocks(const gb_linearized6* lin, double error_scale, double* G11 /*36*/, double* G12 /*36*/, double* g1 /*6*/, double* G22 /*36*/, double* g2 /*6*/, double* f);
+GB_API gb_status gb_slab_row_hessian_blocks(const float* slab_row /* GB_SLAB_STRIDE */, double error_scale, double* G11, double* G12, double* g1, double* G22, double* g2, double* f, double* num_inliers);
+
 /* Prepared batch: the same sweep with its descriptor table resident on the device, split into
  * upload / launch / fetch so that callers (the bench, the multi-GPU sweep) can keep everything in HBM.
  *   pair_index (may be NULL): factor -> row of a caller-owned fp32 slab [num_pairs][GB_SLAB_STRIDE];
@@ -130,7 +146,6 @@ GB_API gb_status gb_factor_set_error(gb_ctx* ctx, size_t num_factors, gb_factor*
  *   (levels of the same pair sum there), which is the buffer the multi-GPU sweep all-reduces
  *   over NCCL.  Slab row: H_tt upper(21) H_ts(36, column-major) H_ss upper(21) b_t(6) b_s(6)
  *   error num_inliers, padded to GB_SLAB_STRIDE floats. */
-#define GB_SLAB_STRIDE 96
 GB_API gb_status gb_sweep_create(gb_ctx* ctx, size_t num_factors, gb_factor* const* factors, const int32_t* pair_index, gb_sweep** out);
 GB_API gb_status gb_sweep_destroy(gb_sweep* sweep);
 GB_API gb_status gb_sweep_attach_slab(gb_sweep* sweep, void* device_slab_f32, size_t num_pairs);

@@ -3,28 +3,47 @@
 // and call order as the reference call sites; every method forwards to the C-ABI of include/glim_b200.h.
 //
 //   gtsam_points::CUDAStream / StreamTempBufferRoundRobin     src/glim/odometry/odometry_estimation_gpu.cpp:76-77, :139-141
-//   gtsam_points::PointCloudGPU::clone(frame[, stream])      src/glim/odometry/odometry_estimation_gpu.cpp:96; src/glim/mapping/sub_mapping.cpp:168
-//   gtsam_points::GaussianVoxelMapGPU(res, 8192*2, 10, 1e-3, stream)::insert(frame)   odometry_estimation_gpu.cpp:103-104
+//   gtsam_points::PointCloud{,CPU,GPU} (points, covs, normals, times, intensities, *_gpu, has_*())
+//                                                            src/glim/odometry/odometry_estimation_imu.cpp:322-328; src/glim/mapping/sub_mapping.cpp:165
+//   gtsam_points::PointCloudGPU::clone(frame[, stream])      src/glim/odometry/odometry_estimation_gpu.cpp:96; src/glim/mapping/sub_mapping.cpp:168, :393
+//   gtsam_points::GaussianVoxelMapGPU(res, 8192*2, 10, 1e-3, stream)::insert(frame)   odometry_estimation_gpu.cpp:103-104; global_mapping.cpp:265 (1 argument)
 //   gtsam_points::IntegratedVGICPFactorGPU(key | pose, key, voxelmap, frame, stream, buffer)   odometry_estimation_gpu.cpp:144, :161
 //   gtsam_points::NonlinearFactorSetGPU::add / linearize    odometry_estimation_gpu.cpp:383-386
 //   gtsam_points::overlap_gpu / overlap_auto                 odometry_estimation_gpu.cpp:231, :248; src/glim/mapping/global_mapping.cpp:448
 //   gtsam_points::median_distance                            odometry_estimation_gpu.cpp:91
 //
+// Ownership and threading (what a drop-in must get right, and round 1 did not):
+//   * PointCloudGPU OWNS its host data.  GLIM replaces the only owner of a frame with its clone
+//     (`new_frame->frame = PointCloudGPU::clone(*new_frame->frame)`, odometry_estimation_gpu.cpp:96; sub_mapping.cpp:168;
+//     global_mapping.cpp:253) and keeps reading frame->points afterwards (median_distance, deskewing, viewer): clone()
+//     deep-copies points / covs / normals / times / intensities, as gtsam_points' own PointCloudGPU (a PointCloudCPU) does.
+//   * Work is bound to the stream the CALLER passes.  CUDAStream and StreamTempBufferRoundRobin each own a context (= a
+//     gb_ctx = one CUDA stream + scratch arena); the raw `CUstream_st*` they hand to GLIM is looked up again when GLIM passes
+//     it back into clone() / GaussianVoxelMapGPU() / IntegratedVGICPFactorGPU() / overlap_gpu().  A call without a stream
+//     (clone(frame), GaussianVoxelMapGPU(resolution), overlap_auto) runs on the calling thread's default context.
+//   * Frames migrate between GLIM's module threads (odometry -> sub-mapping -> global mapping:
+//     async_sub_mapping.cpp:8, async_global_mapping.cpp:24).  A factor may therefore combine a voxel map and a cloud that
+//     were uploaded through different contexts, and a factor set may mix such factors: device memory is shared, every
+//     upload / build call returns only after its stream has drained, and each gb_ctx serialises its callers with a mutex.
+//
 // Two build modes:
 //   * default: self-contained.  Poses are `Pose` (16 doubles, column-major == Eigen::Isometry3d::data()), keys are
-//     uint64_t, `Values` is std::map<Key, Pose>, and linearize() returns the raw gb_linearized6 blocks.  This is
-//     what tests/cpp/ compiles and runs here (GTSAM / Eigen are not installed in this environment).
-//   * -DGLIM_B200_WITH_GTSAM: IntegratedVGICPFactorGPU derives from gtsam::NonlinearFactor, takes gtsam::Key /
-//     gtsam::Pose3 / gtsam::Values and returns gtsam::HessianFactor exactly as the reference factor does
-//     (SURVEY A.3).  Compile-checked only against the signature stubs of tests/cpp/gtsam_stub.
+//     uint64_t, `Values` is std::map<Key, Pose>, points / covariances are the layout-compatible PODs Vector4d / Matrix4d
+//     below, and linearize() returns the raw gb_linearized6 blocks.  This is what tests/cpp/ compiles and runs here
+//     (GTSAM / Eigen are not installed in this environment).
+//   * -DGLIM_B200_WITH_GTSAM: Vector4d / Matrix4d ARE Eigen's, IntegratedVGICPFactorGPU derives from
+//     gtsam::NonlinearFactor, takes gtsam::Key / gtsam::Pose3 / gtsam::Values and returns gtsam::HessianFactor exactly
+//     as the reference factor does.  Compile-checked only against the signature stubs of tests/cpp/gtsam_stub.
 #pragma once
 
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -54,6 +73,40 @@ inline void check(gb_status st, const char* what) {
   if (st != GB_OK) throw std::runtime_error(std::string(what) + ": " + gb_status_string(st) + ": " + gb_last_error());
 }
 
+#if defined(GLIM_B200_WITH_GTSAM) && defined(EIGEN_WORLD_VERSION)
+using Vector4d = Eigen::Vector4d;
+using Matrix4d = Eigen::Matrix4d;
+using Vector3f = Eigen::Vector3f;
+using Matrix3f = Eigen::Matrix3f;
+#else
+/// Layout-compatible stand-ins for Eigen::Vector4d (32 B) / Eigen::Matrix4d (128 B, column-major) / Vector3f / Matrix3f
+/// (standard_viewer_mem.cpp:34-58), with the accessors GLIM uses on frame->points[i] / frame->covs[i].
+struct alignas(16) Vector4d {
+  double v[4];
+  double& operator[](int i) { return v[i]; }
+  double operator[](int i) const { return v[i]; }
+  double& operator()(int i) { return v[i]; }
+  double operator()(int i) const { return v[i]; }
+  double x() const { return v[0]; }
+  double y() const { return v[1]; }
+  double z() const { return v[2]; }
+  double w() const { return v[3]; }
+  const double* data() const { return v; }
+  double* data() { return v; }
+  double norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]); }
+};
+struct alignas(16) Matrix4d {
+  double v[16];
+  double& operator()(int r, int c) { return v[c * 4 + r]; }
+  double operator()(int r, int c) const { return v[c * 4 + r]; }
+  const double* data() const { return v; }
+  double* data() { return v; }
+};
+struct Vector3f { float v[3]; };
+struct Matrix3f { float v[9]; };
+#endif
+static_assert(sizeof(Vector4d) == 32 && sizeof(Matrix4d) == 128, "host element layout (standard_viewer_mem.cpp:34-41)");
+
 /// 4x4 rigid transform, 16 doubles column-major (bit-compatible with Eigen::Isometry3d::data()).
 struct Pose {
   std::array<double, 16> m{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}};
@@ -80,27 +133,56 @@ struct Pose {
   }
 };
 
-/// One gb_ctx per thread of execution (the reference drives each module from one executor thread).
+/// A gb_ctx: one CUDA stream + scratch arena + sweep cache.  Thread-safe (the C-ABI serialises callers per context).
 class Context {
 public:
-  explicit Context(int device = 0) { check(gb_ctx_create(device, &ctx_), "gb_ctx_create"); }
-  Context(int device, CUstream_st* stream) { check(gb_ctx_create_on_stream(device, stream, &ctx_), "gb_ctx_create_on_stream"); }
-  ~Context() { gb_ctx_destroy(ctx_); }
+  explicit Context(int device = 0) {
+    check(gb_ctx_create(device, &ctx_), "gb_ctx_create");
+    std::lock_guard<std::mutex> lock(registry_mutex());
+    registry()[gb_ctx_stream(ctx_)] = ctx_;
+  }
+  ~Context() {
+    {
+      std::lock_guard<std::mutex> lock(registry_mutex());
+      registry().erase(gb_ctx_stream(ctx_));
+    }
+    gb_ctx_destroy(ctx_);
+  }
   Context(const Context&) = delete;
   Context& operator=(const Context&) = delete;
   gb_ctx* get() const { return ctx_; }
-  static std::shared_ptr<Context> default_context() {
+  CUstream_st* stream() const { return static_cast<CUstream_st*>(gb_ctx_stream(ctx_)); }
+
+  /// the calling thread's default context (calls that carry no stream)
+  static gb_ctx* default_ctx() {
     static thread_local std::shared_ptr<Context> c = std::make_shared<Context>(0);
-    return c;
+    return c->get();
+  }
+  /// the context that owns `stream` (a handle obtained from CUDAStream / StreamTempBufferRoundRobin), or the calling
+  /// thread's default context for a null / foreign stream
+  static gb_ctx* of_stream(CUstream_st* stream) {
+    if (stream) {
+      std::lock_guard<std::mutex> lock(registry_mutex());
+      auto it = registry().find(static_cast<void*>(stream));
+      if (it != registry().end()) return it->second;
+    }
+    return default_ctx();
   }
 
 private:
+  static std::mutex& registry_mutex() { static std::mutex m; return m; }
+  static std::map<void*, gb_ctx*>& registry() { static std::map<void*, gb_ctx*> r; return r; }
   gb_ctx* ctx_ = nullptr;
 };
 
 }  // namespace glim_b200
 
 namespace gtsam_points {
+
+using glim_b200::Matrix3f;
+using glim_b200::Matrix4d;
+using glim_b200::Vector3f;
+using glim_b200::Vector4d;
 
 #ifdef GLIM_B200_WITH_GTSAM
 using Key = gtsam::Key;
@@ -110,79 +192,145 @@ using Key = std::uint64_t;
 using Values = std::map<Key, glim_b200::Pose>;
 #endif
 
-/// gtsam_points::CUDAStream: owns the context (stream) the frame's GPU work is ordered on.
+/// gtsam_points::CUDAStream: owns a stream (context); converts to the raw handle GLIM passes around (`*stream`).
 class CUDAStream {
 public:
   CUDAStream() : ctx_(std::make_shared<glim_b200::Context>(0)) {}
-  operator CUstream_st*() const { return static_cast<CUstream_st*>(gb_ctx_stream(ctx_->get())); }
-  const std::shared_ptr<glim_b200::Context>& context() const { return ctx_; }
+  operator CUstream_st*() const { return ctx_->stream(); }
+  CUstream_st* get_stream() const { return ctx_->stream(); }
+  void sync() const { glim_b200::check(gb_ctx_synchronize(ctx_->get()), "gb_ctx_synchronize"); }
 
 private:
   std::shared_ptr<glim_b200::Context> ctx_;
 };
 
-/// gtsam_points::TempBufferManager: scratch is owned by the gb_ctx arena, the handle only keeps it alive.
+/// gtsam_points::TempBufferManager: scratch is owned by the gb_ctx arena; the handle exists for the signature.
 class TempBufferManager {
 public:
-  explicit TempBufferManager(std::shared_ptr<glim_b200::Context> ctx) : ctx(std::move(ctx)) {}
-  std::shared_ptr<glim_b200::Context> ctx;
+  TempBufferManager() = default;
 };
 
 /// gtsam_points::StreamTempBufferRoundRobin(N): the reference hands out N (stream, buffer) pairs so that N factors
-/// can run concurrently.  The fused sweep runs all factors of a graph in ONE launch, so every pair maps to the
-/// same context; N is accepted and ignored.
+/// can run concurrently.  The fused sweep runs all factors of a graph in ONE launch, so every pair is the module's one
+/// stream; N is accepted and ignored.
 class StreamTempBufferRoundRobin {
 public:
-  explicit StreamTempBufferRoundRobin(int /*num_streams*/ = 8) : ctx_(std::make_shared<glim_b200::Context>(0)), buffer_(std::make_shared<TempBufferManager>(ctx_)) {}
-  std::pair<CUstream_st*, std::shared_ptr<TempBufferManager>> get_stream_buffer() { return {static_cast<CUstream_st*>(gb_ctx_stream(ctx_->get())), buffer_}; }
-  const std::shared_ptr<glim_b200::Context>& context() const { return ctx_; }
+  explicit StreamTempBufferRoundRobin(int /*num_streams*/ = 8) : ctx_(std::make_shared<glim_b200::Context>(0)), buffer_(std::make_shared<TempBufferManager>()) {}
+  std::pair<CUstream_st*, std::shared_ptr<TempBufferManager>> get_stream_buffer() { return {ctx_->stream(), buffer_}; }
 
 private:
   std::shared_ptr<glim_b200::Context> ctx_;
   std::shared_ptr<TempBufferManager> buffer_;
 };
 
-/// gtsam_points::PointCloud (host view: the members GLIM reads, include/glim/odometry/estimation_frame.hpp:103).
+/// gtsam_points::PointCloud: non-owning view with the members GLIM reads (include/glim/odometry/estimation_frame.hpp:103;
+/// standard_viewer_mem.cpp:34-58).
 struct PointCloud {
   using Ptr = std::shared_ptr<PointCloud>;
   using ConstPtr = std::shared_ptr<const PointCloud>;
+  PointCloud() = default;
   virtual ~PointCloud() = default;
   std::size_t size() const { return num_points; }
+  bool has_times() const { return times != nullptr; }
   bool has_points() const { return points != nullptr; }
-  bool has_covs() const { return covs != nullptr; }
   bool has_normals() const { return normals != nullptr; }
+  bool has_covs() const { return covs != nullptr; }
+  bool has_intensities() const { return intensities != nullptr; }
+  bool has_times_gpu() const { return times_gpu != nullptr; }
+  bool has_points_gpu() const { return points_gpu != nullptr; }
+  bool has_normals_gpu() const { return normals_gpu != nullptr; }
+  bool has_covs_gpu() const { return covs_gpu != nullptr; }
+  bool has_intensities_gpu() const { return intensities_gpu != nullptr; }
+
   std::size_t num_points = 0;
-  const double* points = nullptr;   // N x Vector4d
-  const double* covs = nullptr;     // N x Matrix4d, column-major
-  const double* normals = nullptr;  // N x Vector4d
+  double* times = nullptr;
+  Vector4d* points = nullptr;
+  Vector4d* normals = nullptr;
+  Matrix4d* covs = nullptr;
+  double* intensities = nullptr;
+  // Device side.  Non-null == "this frame has GPU data" (the only way GLIM uses them: sub_mapping.cpp:165,
+  // global_mapping.cpp:252, :330, standard_viewer_mem.cpp:49-58).  They point into the gb_cloud's planes
+  // ({x y z c00} float4 / {c01 c02 c11 c12} float4 / c22), NOT at dense Vector3f / Matrix3f arrays.
+  float* times_gpu = nullptr;
+  Vector3f* points_gpu = nullptr;
+  Vector3f* normals_gpu = nullptr;
+  Matrix3f* covs_gpu = nullptr;
+  float* intensities_gpu = nullptr;
 };
 
-/// gtsam_points::PointCloudGPU: device copy (fp32) of a PointCloud.
-class PointCloudGPU : public PointCloud {
+/// gtsam_points::PointCloudCPU: owns its arrays.
+struct PointCloudCPU : public PointCloud {
+  using Ptr = std::shared_ptr<PointCloudCPU>;
+  using ConstPtr = std::shared_ptr<const PointCloudCPU>;
+  PointCloudCPU() = default;
+  /// deep copy of whatever attributes `frame` has
+  explicit PointCloudCPU(const PointCloud& frame) { copy_host(frame); }
+  PointCloudCPU(const PointCloudCPU& other) : PointCloud() { copy_host(other); }
+  PointCloudCPU& operator=(const PointCloudCPU&) = delete;
+
+  template <typename T>
+  void add_points(const T* pts, std::size_t n) {  // N x 4 doubles (w = 1)
+    points_storage.resize(n);
+    if (n) std::memcpy(static_cast<void*>(points_storage.data()), pts, sizeof(Vector4d) * n);
+    points = points_storage.data();
+    num_points = n;
+  }
+  void add_covs(const double* c, std::size_t n) {  // N x 16 doubles, column-major 4x4
+    covs_storage.resize(n);
+    if (n) std::memcpy(static_cast<void*>(covs_storage.data()), c, sizeof(Matrix4d) * n);
+    covs = covs_storage.data();
+  }
+  void add_normals(const double* nr, std::size_t n) {
+    normals_storage.resize(n);
+    if (n) std::memcpy(static_cast<void*>(normals_storage.data()), nr, sizeof(Vector4d) * n);
+    normals = normals_storage.data();
+  }
+  void add_times(const double* t, std::size_t n) { times_storage.assign(t, t + n); times = times_storage.data(); }
+  void add_intensities(const double* t, std::size_t n) { intensities_storage.assign(t, t + n); intensities = intensities_storage.data(); }
+
+  std::vector<double> times_storage;
+  std::vector<Vector4d> points_storage;
+  std::vector<Vector4d> normals_storage;
+  std::vector<Matrix4d> covs_storage;
+  std::vector<double> intensities_storage;
+
+protected:
+  void copy_host(const PointCloud& frame) {
+    num_points = frame.num_points;
+    if (frame.points) add_points(reinterpret_cast<const double*>(frame.points), frame.num_points);
+    if (frame.covs) add_covs(reinterpret_cast<const double*>(frame.covs), frame.num_points);
+    if (frame.normals) add_normals(reinterpret_cast<const double*>(frame.normals), frame.num_points);
+    if (frame.times) add_times(frame.times, frame.num_points);
+    if (frame.intensities) add_intensities(frame.intensities, frame.num_points);
+  }
+};
+
+/// gtsam_points::PointCloudGPU: a PointCloudCPU (owning deep copy of the host data) + the fp32 device copy.
+class PointCloudGPU : public PointCloudCPU {
 public:
   using Ptr = std::shared_ptr<PointCloudGPU>;
   using ConstPtr = std::shared_ptr<const PointCloudGPU>;
   ~PointCloudGPU() override { gb_cloud_destroy(cloud_); }
+  PointCloudGPU(const PointCloudGPU&) = delete;
+  PointCloudGPU& operator=(const PointCloudGPU&) = delete;
 
-  static Ptr clone(const PointCloud& frame, const std::shared_ptr<glim_b200::Context>& ctx = glim_b200::Context::default_context()) {
+  /// clone(frame): odometry_estimation_gpu.cpp:96, global_mapping.cpp:253, :260.  clone(frame, stream): sub_mapping.cpp:168, :393.
+  static Ptr clone(const PointCloud& frame, CUstream_st* stream = nullptr) {
     Ptr c(new PointCloudGPU);
-    c->ctx_ = ctx;
-    c->num_points = frame.num_points;
-    c->points = frame.points;
-    c->covs = frame.covs;
-    c->normals = frame.normals;
-    glim_b200::check(gb_cloud_upload(ctx->get(), frame.num_points, frame.points, frame.covs, frame.normals, &c->cloud_), "gb_cloud_upload");
+    c->copy_host(frame);  // OWNING copy: the caller is about to drop `frame`
+    gb_ctx* ctx = glim_b200::Context::of_stream(stream);
+    glim_b200::check(gb_cloud_upload(ctx, c->num_points, reinterpret_cast<const double*>(c->points), reinterpret_cast<const double*>(c->covs), reinterpret_cast<const double*>(c->normals), &c->cloud_), "gb_cloud_upload");
+    void *p0 = nullptr, *p1 = nullptr, *nr = nullptr;
+    glim_b200::check(gb_cloud_device_ptrs(c->cloud_, &p0, &p1, nullptr, &nr), "gb_cloud_device_ptrs");
+    c->points_gpu = static_cast<Vector3f*>(p0);
+    c->covs_gpu = c->covs ? static_cast<Matrix3f*>(p1) : nullptr;
+    c->normals_gpu = static_cast<Vector3f*>(nr);
     return c;
   }
-  static Ptr clone(const PointCloud& frame, const CUDAStream& stream) { return clone(frame, stream.context()); }
-  bool has_points_gpu() const { return cloud_ != nullptr; }
-  bool has_covs_gpu() const { return cloud_ != nullptr && covs != nullptr; }
   gb_cloud* handle() const { return cloud_; }
-  const std::shared_ptr<glim_b200::Context>& context() const { return ctx_; }
 
 private:
   PointCloudGPU() = default;
-  std::shared_ptr<glim_b200::Context> ctx_;
   gb_cloud* cloud_ = nullptr;
 };
 
@@ -198,6 +346,7 @@ struct GaussianVoxelMap {
   using ConstPtr = std::shared_ptr<const GaussianVoxelMap>;
   virtual ~GaussianVoxelMap() = default;
   virtual double voxel_resolution() const = 0;
+  virtual void insert(const PointCloud& frame) = 0;
 };
 
 /// gtsam_points::GaussianVoxelMapGPU(resolution, init_num_buckets, max_bucket_scan_count, target_points_drop_rate, stream)
@@ -205,18 +354,20 @@ class GaussianVoxelMapGPU : public GaussianVoxelMap {
 public:
   using Ptr = std::shared_ptr<GaussianVoxelMapGPU>;
   using ConstPtr = std::shared_ptr<const GaussianVoxelMapGPU>;
-  explicit GaussianVoxelMapGPU(float resolution, int init_num_buckets = 8192 * 2, int max_bucket_scan_count = 10, double target_points_drop_rate = 1e-3, CUstream_st* /*stream*/ = nullptr)
-  : resolution_(resolution), init_num_buckets_(init_num_buckets), max_bucket_scan_count_(max_bucket_scan_count), target_points_drop_rate_(target_points_drop_rate) {}
+  explicit GaussianVoxelMapGPU(float resolution, int init_num_buckets = 8192 * 2, int max_bucket_scan_count = 10, double target_points_drop_rate = 1e-3, CUstream_st* stream = nullptr)
+  : resolution_(resolution), init_num_buckets_(init_num_buckets), max_bucket_scan_count_(max_bucket_scan_count), target_points_drop_rate_(target_points_drop_rate), stream_(stream) {}
   ~GaussianVoxelMapGPU() override { gb_voxelmap_destroy(map_); }
+  GaussianVoxelMapGPU(const GaussianVoxelMapGPU&) = delete;
+  GaussianVoxelMapGPU& operator=(const GaussianVoxelMapGPU&) = delete;
 
   /// insert(frame): `frame` must be (or is uploaded as) a PointCloudGPU; one insert per map, as at every GLIM call site.
-  void insert(const PointCloud& frame) {
+  /// Runs on the stream given to the constructor (the caller's module stream), whatever context uploaded the cloud.
+  void insert(const PointCloud& frame) override {
     if (map_) throw std::runtime_error("GaussianVoxelMapGPU::insert called twice");
     const auto* gpu = dynamic_cast<const PointCloudGPU*>(&frame);
     PointCloudGPU::Ptr tmp;
-    if (!gpu) { tmp = PointCloudGPU::clone(frame); gpu = tmp.get(); }
-    ctx_ = gpu->context();
-    glim_b200::check(gb_voxelmap_build(ctx_->get(), gpu->handle(), resolution_, init_num_buckets_, max_bucket_scan_count_, target_points_drop_rate_, &map_), "gb_voxelmap_build");
+    if (!gpu) { tmp = PointCloudGPU::clone(frame, stream_); gpu = tmp.get(); }
+    glim_b200::check(gb_voxelmap_build(glim_b200::Context::of_stream(stream_), gpu->handle(), resolution_, init_num_buckets_, max_bucket_scan_count_, target_points_drop_rate_, &map_), "gb_voxelmap_build");
     float r = 0.f;
     gb_voxelmap_info(map_, &voxelmap_info.num_voxels, &voxelmap_info.num_buckets, &r);
     voxelmap_info.voxel_resolution = r;
@@ -224,14 +375,13 @@ public:
   }
   double voxel_resolution() const override { return resolution_; }
   gb_voxelmap* handle() const { return map_; }
-  const std::shared_ptr<glim_b200::Context>& context() const { return ctx_; }
   VoxelMapInfo voxelmap_info;
 
 private:
   float resolution_;
   int init_num_buckets_, max_bucket_scan_count_;
   double target_points_drop_rate_;
-  std::shared_ptr<glim_b200::Context> ctx_;
+  CUstream_st* stream_;
   gb_voxelmap* map_ = nullptr;
 };
 
@@ -251,27 +401,27 @@ public:
   using shared_ptr = std::shared_ptr<IntegratedVGICPFactorGPU>;
 
   /// binary: (target_key, source_key, target voxelmap, source frame, stream, buffer)   odometry_estimation_gpu.cpp:144
-  IntegratedVGICPFactorGPU(Key target_key, Key source_key, const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, CUstream_st* = nullptr, std::shared_ptr<TempBufferManager> = nullptr)
+  IntegratedVGICPFactorGPU(Key target_key, Key source_key, const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, CUstream_st* stream = nullptr, std::shared_ptr<TempBufferManager> = nullptr)
 #ifdef GLIM_B200_WITH_GTSAM
   : gtsam::NonlinearFactor(gtsam::KeyVector{target_key, source_key}),
 #else
   :
 #endif
     is_binary_(true), target_key_(target_key), source_key_(source_key) {
-    init(target, source);
+    init(target, source, stream);
   }
   /// unary: (fixed_target_pose, source_key, ...)   odometry_estimation_gpu.cpp:161
 #ifdef GLIM_B200_WITH_GTSAM
-  IntegratedVGICPFactorGPU(const gtsam::Pose3& fixed_target_pose, Key source_key, const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, CUstream_st* = nullptr, std::shared_ptr<TempBufferManager> = nullptr)
+  IntegratedVGICPFactorGPU(const gtsam::Pose3& fixed_target_pose, Key source_key, const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, CUstream_st* stream = nullptr, std::shared_ptr<TempBufferManager> = nullptr)
   : gtsam::NonlinearFactor(gtsam::KeyVector{source_key}), is_binary_(false), target_key_(0), source_key_(source_key) {
     const gtsam::Matrix4 M = fixed_target_pose.matrix();
     for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) fixed_target_pose_(r, c) = M(r, c);
-    init(target, source);
+    init(target, source, stream);
   }
 #else
-  IntegratedVGICPFactorGPU(const glim_b200::Pose& fixed_target_pose, Key source_key, const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, CUstream_st* = nullptr, std::shared_ptr<TempBufferManager> = nullptr)
+  IntegratedVGICPFactorGPU(const glim_b200::Pose& fixed_target_pose, Key source_key, const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, CUstream_st* stream = nullptr, std::shared_ptr<TempBufferManager> = nullptr)
   : is_binary_(false), target_key_(0), source_key_(source_key), fixed_target_pose_(fixed_target_pose) {
-    init(target, source);
+    init(target, source, stream);
   }
 #endif
   ~IntegratedVGICPFactorGPU() { gb_vgicp_factor_destroy(factor_); }
@@ -296,7 +446,9 @@ public:
   std::size_t memory_usage() const { return sizeof(*this); }                           // standard_viewer_mem.cpp:160
   std::size_t memory_usage_gpu() const { return 122 * sizeof(double) + 64; }           // standard_viewer_mem.cpp:161
   double inlier_fraction() const { return source_->size() ? last_num_inliers_ / static_cast<double>(source_->size()) : 0.0; }
+  int num_inliers() const { return static_cast<int>(last_num_inliers_); }
   gb_factor* handle() const { return factor_; }
+  gb_ctx* context() const { return ctx_; }
 
   /// delta = T_target^-1 * T_source
   glim_b200::Pose delta(const Values& values) const {
@@ -335,23 +487,20 @@ public:
     gb_linearized6 L;
     if (self->cached_valid_) { L = self->cached_; self->cached_valid_ = false; } else { L = self->linearize_raw(values).blocks; }
     gtsam::Matrix6 H_tt, H_ss, H_ts;
-    gtsam::Vector6 g_t, g_s;  // HessianFactor takes the NEGATED gradients
-    for (int c = 0; c < 6; c++) {
-      for (int r = 0; r < 6; r++) { H_tt(r, c) = L.H_tt[c * 6 + r]; H_ss(r, c) = L.H_ss[c * 6 + r]; H_ts(r, c) = L.H_ts[c * 6 + r]; }
-      g_t(c) = -L.b_t[c];
-      g_s(c) = -L.b_s[c];
-    }
-    if (is_binary_) return std::make_shared<gtsam::HessianFactor>(target_key_, source_key_, H_tt, H_ts, g_t, H_ss, g_s, GLIM_B200_ERROR_SCALE * L.error);
-    return std::make_shared<gtsam::HessianFactor>(source_key_, H_ss, g_s, GLIM_B200_ERROR_SCALE * L.error);
+    gtsam::Vector6 g_t, g_s;
+    // exactly the reference's hand-off: gb_hessian_blocks negates the gradients and scales the constant term
+    gb_hessian_blocks(&L, GLIM_B200_ERROR_SCALE, &H_tt(0, 0), &H_ts(0, 0), &g_t(0), &H_ss(0, 0), &g_s(0), &L.error);
+    if (is_binary_) return std::make_shared<gtsam::HessianFactor>(target_key_, source_key_, H_tt, H_ts, g_t, H_ss, g_s, L.error);
+    return std::make_shared<gtsam::HessianFactor>(source_key_, H_ss, g_s, L.error);
   }
   gtsam::NonlinearFactor::shared_ptr clone() const override {
     std::shared_ptr<IntegratedVGICPFactorGPU> f;
     if (is_binary_) {
-      f = std::make_shared<IntegratedVGICPFactorGPU>(target_key_, source_key_, target_, source_);
+      f = std::make_shared<IntegratedVGICPFactorGPU>(target_key_, source_key_, target_, source_, stream_);
     } else {
       gtsam::Matrix4 M;
       for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) M(r, c) = fixed_target_pose_(r, c);
-      f = std::make_shared<IntegratedVGICPFactorGPU>(gtsam::Pose3(M), source_key_, target_, source_);
+      f = std::make_shared<IntegratedVGICPFactorGPU>(gtsam::Pose3(M), source_key_, target_, source_, stream_);
     }
     f->set_enable_surface_validation(surface_validation_);
     return f;
@@ -363,7 +512,6 @@ public:
     cached_ = L; cached_valid_ = true; lin_point_ = lin_point; have_lin_point_ = true; last_num_inliers_ = L.num_inliers;
   }
   bool take_cached(gb_linearized6* out) { if (!cached_valid_) return false; *out = cached_; cached_valid_ = false; return true; }
-  const std::shared_ptr<glim_b200::Context>& context() const { return ctx_; }
 
 private:
   static glim_b200::Pose pose_of(const Values& values, Key k) {
@@ -376,18 +524,19 @@ private:
     return values.at(k);
 #endif
   }
-  void init(const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source) {
+  void init(const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, CUstream_st* stream) {
     target_ = std::dynamic_pointer_cast<const GaussianVoxelMapGPU>(target);
     source_ = std::dynamic_pointer_cast<const PointCloudGPU>(source);
     if (!target_ || !target_->handle()) throw std::runtime_error("IntegratedVGICPFactorGPU: target is not a (built) GaussianVoxelMapGPU");
     if (!source_ || !source_->handle()) throw std::runtime_error("IntegratedVGICPFactorGPU: source has no GPU points (PointCloudGPU::clone it first)");
-    ctx_ = source_->context();
+    stream_ = stream;
+    ctx_ = glim_b200::Context::of_stream(stream);  // the CALLER's stream: the module that builds the graph also linearizes it
     recreate();
   }
   void recreate() {
     if (factor_) gb_vgicp_factor_destroy(factor_);
     factor_ = nullptr;
-    glim_b200::check(gb_vgicp_factor_create(ctx_->get(), target_->handle(), source_->handle(), surface_validation_ ? GB_FACTOR_SURFACE_VALIDATION : 0, &factor_), "gb_vgicp_factor_create");
+    glim_b200::check(gb_vgicp_factor_create(ctx_, target_->handle(), source_->handle(), surface_validation_ ? GB_FACTOR_SURFACE_VALIDATION : 0, &factor_), "gb_vgicp_factor_create");
   }
 
   bool is_binary_;
@@ -395,7 +544,8 @@ private:
   glim_b200::Pose fixed_target_pose_;
   GaussianVoxelMapGPU::ConstPtr target_;  // kept alive, as the reference factor keeps shared_ptrs
   PointCloudGPU::ConstPtr source_;
-  std::shared_ptr<glim_b200::Context> ctx_;
+  CUstream_st* stream_ = nullptr;
+  gb_ctx* ctx_ = nullptr;
   gb_factor* factor_ = nullptr;
   bool surface_validation_ = false;
   glim_b200::Pose lin_point_;
@@ -407,7 +557,8 @@ private:
 
 /// gtsam_points::NonlinearFactorSetGPU: add(graph) collects the GPU factors; linearize(values) runs ONE fused sweep
 /// (F x 128 B of poses down, F records up) and caches every factor's result for the GTSAM linearize() that follows
-/// (odometry_estimation_gpu.cpp:383-386).
+/// (odometry_estimation_gpu.cpp:383-386).  The sweep runs on the context of the first factor, i.e. on the stream the
+/// module passed when it built its factors; the factors may reference clouds / maps uploaded through other contexts.
 class NonlinearFactorSetGPU {
 public:
   void clear() { factors_.clear(); }
@@ -439,7 +590,7 @@ public:
       std::copy(deltas[i].m.begin(), deltas[i].m.end(), T.begin() + 16 * i);
     }
     results_.resize(F);
-    glim_b200::check(gb_factor_set_linearize(factors_[0]->context()->get(), F, handles.data(), T.data(), results_.data()), "gb_factor_set_linearize");
+    glim_b200::check(gb_factor_set_linearize(factors_[0]->context(), F, handles.data(), T.data(), results_.data()), "gb_factor_set_linearize");
     for (std::size_t i = 0; i < F; i++) factors_[i]->set_cached(results_[i], deltas[i]);
   }
   const std::vector<gb_linearized6>& results() const { return results_; }
@@ -450,17 +601,17 @@ private:
 };
 
 /// gtsam_points::overlap_gpu(voxelmap, source, delta, stream)   odometry_estimation_gpu.cpp:248
-inline double overlap_gpu(const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, const glim_b200::Pose& delta, CUstream_st* = nullptr) {
+inline double overlap_gpu(const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, const glim_b200::Pose& delta, CUstream_st* stream = nullptr) {
   const auto t = std::dynamic_pointer_cast<const GaussianVoxelMapGPU>(target);
   const auto s = std::dynamic_pointer_cast<const PointCloudGPU>(source);
   if (!t || !s) throw std::runtime_error("overlap_gpu: GPU voxel map / GPU point cloud required");
   const gb_voxelmap* maps[1] = {t->handle()};
   double ov = 0.0;
-  glim_b200::check(gb_overlap(s->context()->get(), 1, maps, s->handle(), delta.data(), &ov), "gb_overlap");
+  glim_b200::check(gb_overlap(glim_b200::Context::of_stream(stream), 1, maps, s->handle(), delta.data(), &ov), "gb_overlap");
   return ov;
 }
 /// gtsam_points::overlap_gpu(voxelmaps, source, deltas, stream)   odometry_estimation_gpu.cpp:231
-inline double overlap_gpu(const std::vector<GaussianVoxelMap::ConstPtr>& targets, const PointCloud::ConstPtr& source, const std::vector<glim_b200::Pose>& deltas, CUstream_st* = nullptr) {
+inline double overlap_gpu(const std::vector<GaussianVoxelMap::ConstPtr>& targets, const PointCloud::ConstPtr& source, const std::vector<glim_b200::Pose>& deltas, CUstream_st* stream = nullptr) {
   const auto s = std::dynamic_pointer_cast<const PointCloudGPU>(source);
   if (!s || targets.size() != deltas.size()) throw std::runtime_error("overlap_gpu: bad arguments");
   std::vector<const gb_voxelmap*> maps(targets.size());
@@ -472,7 +623,7 @@ inline double overlap_gpu(const std::vector<GaussianVoxelMap::ConstPtr>& targets
     std::copy(deltas[i].m.begin(), deltas[i].m.end(), T.begin() + 16 * i);
   }
   double ov = 0.0;
-  glim_b200::check(gb_overlap(s->context()->get(), maps.size(), maps.data(), s->handle(), T.data(), &ov), "gb_overlap");
+  glim_b200::check(gb_overlap(glim_b200::Context::of_stream(stream), maps.size(), maps.data(), s->handle(), T.data(), &ov), "gb_overlap");
   return ov;
 }
 /// gtsam_points::overlap_auto: GPU voxel maps dispatch to overlap_gpu (sub_mapping.cpp:252; global_mapping.cpp:322, :448)
@@ -485,7 +636,7 @@ inline double median_distance(const PointCloud::ConstPtr& frame, int max_scan_co
   const std::size_t step = std::max<std::size_t>(1, n / static_cast<std::size_t>(max_scan_count));
   std::vector<double> d;
   for (std::size_t i = 0; i < n; i += step) {
-    const double* p = frame->points + 4 * i;
+    const double* p = reinterpret_cast<const double*>(&frame->points[i]);
     d.push_back(std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
   }
   std::nth_element(d.begin(), d.begin() + d.size() / 2, d.end());

@@ -14,6 +14,9 @@ import bench  # noqa: E402
 
 CONFIGS = [
     ("v3", {"GB_KERNEL": "3"}),
+    ("v5 ipw6", {"GB_KERNEL": "5", "GB_ITEMS_PER_WARP": "6"}),
+    ("v5 ipw2", {"GB_KERNEL": "5", "GB_ITEMS_PER_WARP": "2"}),
+    ("v5 ipw1", {"GB_KERNEL": "5", "GB_ITEMS_PER_WARP": "1"}),
     ("v4 T128 ipw4", {"GB_KERNEL": "4", "GB_STAGE": "128", "GB_ITEMS_PER_WARP": "4"}),
     ("v4 T128 ipw1", {"GB_KERNEL": "4", "GB_STAGE": "128", "GB_ITEMS_PER_WARP": "1"}),
     ("v4 T128 ipw2", {"GB_KERNEL": "4", "GB_STAGE": "128", "GB_ITEMS_PER_WARP": "2"}),

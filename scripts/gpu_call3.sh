@@ -1,0 +1,8 @@
+# round 2, call 3: v5 kernel + fixed v4, shim replay under ASan
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
+AB_CONFIGS="v3,v5 ipw6,v5 ipw2,v5 ipw1,v4 T128 ipw4,v4 T128 ipw1,v4 T64 ipw4" timeout 600 python scripts/ab_sweep.py > gpurun_out/ab_r02b.txt 2> gpurun_out/ab_r02b.err; echo "ab rc=$?"; grep -v "^#" gpurun_out/ab_r02b.txt | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print(d['workload'][:12].ljust(12), d['config'].ljust(14), str(d['M_pf_s']).rjust(8), str(d['us_per_launch']).rjust(9), d['frac'], d['items_grid'], d['same_as_first'])"
+tail -3 gpurun_out/ab_r02b.err

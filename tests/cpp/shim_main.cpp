@@ -34,12 +34,16 @@ int main(int argc, char** argv) {
   try {
     CUDAStream stream;                               // odometry_estimation_gpu.cpp:76
     StreamTempBufferRoundRobin roundrobin;           // :77
-    PointCloud::Ptr host[2];
-    PointCloudGPU::Ptr frames[2];
+    PointCloud::ConstPtr frames[2];
+    double md = 0.0;
     for (int k = 0; k < 2; k++) {
-      host[k] = std::make_shared<PointCloud>();
-      host[k]->num_points = (size_t)n[k]; host[k]->points = pts[k].data(); host[k]->covs = covs[k].data();
-      frames[k] = PointCloudGPU::clone(*host[k], roundrobin.context());   // :96
+      auto host = std::make_shared<PointCloudCPU>();
+      host->add_points(pts[k].data(), (size_t)n[k]);
+      host->add_covs(covs[k].data(), (size_t)n[k]);
+      frames[k] = host;
+      md = median_distance(frames[k], 256);                          // :91
+      frames[k] = PointCloudGPU::clone(*frames[k]);                  // :96  (the host frame dies here: clone owns a copy)
+      if (md != median_distance(frames[k], 256)) throw std::runtime_error("clone changed the host data");
     }
     // create_frame: voxelmap_levels maps with resolution * scaling^level   (:97-106)
     std::vector<GaussianVoxelMap::Ptr> voxelmaps;
@@ -65,8 +69,6 @@ int main(int argc, char** argv) {
     set.linearize(values);
     const double err = graph[3]->error(values);
     const double ov = overlap_gpu(std::vector<GaussianVoxelMap::ConstPtr>{voxelmaps[1]}, frames[1], std::vector<glim_b200::Pose>{Tt.inverse() * Ts}, stream);   // :231
-    const double md = median_distance(host[1], 256);  // :91
-    (void)md;
 
     FILE* fo = fopen(argv[2], "wb");
     fwrite(set.results().data(), sizeof(gb_linearized6), 4, fo);

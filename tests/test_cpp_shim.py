@@ -26,6 +26,33 @@ def test_header_is_plain_c(tmp_path):
 def test_shims_compile_standalone_and_gtsam_mode(tmp_path):
     subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{INC}", "-c", os.path.join(CPP, "shim_main.cpp"), "-o", str(tmp_path / "a.o")])
     subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{INC}", f"-I{os.path.join(CPP, 'gtsam_stub')}", "-c", os.path.join(CPP, "gtsam_mode_check.cpp"), "-o", str(tmp_path / "b.o")])
+    subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-pthread", f"-I{INC}", "-c", os.path.join(CPP, "replay_glim.cpp"), "-o", str(tmp_path / "c.o")])
+
+
+def test_solver_handoff_blocks_host_only():
+    """gb_hessian_blocks / gb_slab_row_hessian_blocks (global_mapping.cpp:492-501): HessianFactor(k_t, k_s, H_tt, H_ts,
+    -b_t, H_ss, -b_s, scale * error) from a record and from a pair-slab row; host-only helpers, no device needed."""
+    from glim_b200 import capi, gpu, multi_gpu
+
+    rng = np.random.default_rng(3)
+    rec = np.zeros(1, gpu.LIN_DTYPE)
+    A = rng.normal(size=(12, 12))
+    H = A @ A.T
+    rec[0]["H_tt"] = H[:6, :6].T.reshape(36)
+    rec[0]["H_ts"] = H[:6, 6:].T.reshape(36)
+    rec[0]["H_ss"] = H[6:, 6:].T.reshape(36)
+    rec[0]["b_t"], rec[0]["b_s"] = rng.normal(size=6), rng.normal(size=6)
+    rec[0]["error"], rec[0]["num_inliers"] = 3.5, 1234.0
+    outs = [np.zeros(36), np.zeros(36), np.zeros(6), np.zeros(36), np.zeros(6), np.zeros(1)]
+    capi.check(capi.lib().gb_hessian_blocks(capi.ptr(rec), 0.5, *[capi.ptr(o) for o in outs]))
+    assert np.array_equal(outs[0].reshape(6, 6).T, H[:6, :6]) and np.array_equal(outs[1].reshape(6, 6).T, H[:6, 6:]) and np.array_equal(outs[3].reshape(6, 6).T, H[6:, 6:])
+    assert np.array_equal(outs[2], -rec[0]["b_t"]) and np.array_equal(outs[4], -rec[0]["b_s"]) and outs[5][0] == 0.5 * 3.5
+    row = multi_gpu.pack_slab_row(gpu.unpack_linearized(rec[0]))
+    outs2 = [np.zeros(36), np.zeros(36), np.zeros(6), np.zeros(36), np.zeros(6), np.zeros(1), np.zeros(1)]
+    capi.check(capi.lib().gb_slab_row_hessian_blocks(capi.ptr(row), 0.5, *[capi.ptr(o) for o in outs2]))
+    for a, b in zip(outs, outs2[:6]):
+        assert np.allclose(a, b, rtol=1e-6, atol=1e-6)
+    assert outs2[6][0] == 1234.0
 
 
 @pytest.mark.gpu
@@ -72,3 +99,53 @@ def test_cpp_shim_reproduces_oracle(tmp_path):
         if level == 1:
             assert abs(err - ref["error"]) < util.REL_TOL * ref["error"]
             assert ov == oracle.overlap_gpumap([m], xyz1, [delta])
+
+
+@pytest.mark.gpu
+def test_replay_glim_modules_across_threads_under_asan(tmp_path):
+    """The exact statements of odometry_estimation_gpu.cpp:96-104, sub_mapping.cpp:165-169 / :393-399 and
+    global_mapping.cpp:239-266 / :322-335, one module per thread, frames handed from module to module, built with
+    AddressSanitizer: clones own their host data (reading frame->points after `frame = clone(*frame)` is legal), work runs on
+    the stream each module passes, factor sets mix clouds / maps uploaded by different module threads."""
+    from glim_b200 import capi, synth
+    from oracle import oracle
+    from tests import util
+
+    exe = tmp_path / "replay_glim"
+    libdir = os.path.dirname(capi.SO_PATH)
+    subprocess.check_call([GXX, "-std=c++17", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-pthread", f"-I{INC}", os.path.join(CPP, "replay_glim.cpp"), "-o", str(exe), f"-L{libdir}", "-lglim_b200", f"-Wl,-rpath,{libdir}"])
+    pair = util.scan_pair()
+    Tt = synth.pose(3.0, -1.0, 0.2, 0.4, 0.01, -0.02)
+    T = synth.perturb(synth.inv_pose(pair["poses"][0]) @ pair["poses"][1], synth.rng_for(22), 0.01, 0.05)
+    Ts = Tt @ T
+    inp = tmp_path / "in.bin"
+    with open(inp, "wb") as f:
+        np.array([len(pair["points"][0]), len(pair["points"][1])], np.int32).tofile(f)
+        for k in (0, 1):
+            np.ascontiguousarray(pair["points"][k]).tofile(f)
+            util.cov_colmajor16(pair["covs"][k]).tofile(f)
+        capi.pose16(Tt).tofile(f)
+        capi.pose16(Ts).tofile(f)
+    out = tmp_path / "out.bin"
+    env = dict(os.environ, ASAN_OPTIONS="protect_shadow_gap=0:detect_leaks=0:abort_on_error=0")
+    r = subprocess.run([str(exe), str(inp), str(out)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    assert "AddressSanitizer" not in r.stderr
+    raw = np.fromfile(out, dtype=np.uint8)
+    recs = np.frombuffer(raw[: 6 * 976].tobytes(), dtype=np.float64).reshape(6, 122)
+    ov = np.frombuffer(raw[6 * 976 : 6 * 976 + 24].tobytes(), dtype=np.float64)
+    md = np.frombuffer(raw[6 * 976 + 24 : 6 * 976 + 40].tobytes(), dtype=np.float64)
+    assert md[0] == md[1] > 0  # host data survived clone-of-clone and the death of every earlier owner
+    xyz0, cov0 = oracle.pack_cloud(pair["points"][0], util.cov_colmajor16(pair["covs"][0]))
+    xyz1, cov1 = oracle.pack_cloud(pair["points"][1], util.cov_colmajor16(pair["covs"][1]))
+    delta = synth.inv_pose(Tt) @ Ts
+    for level, res in enumerate((0.25, 0.5)):
+        m = oracle.GpuMap(xyz0, cov0, res)
+        ref = oracle.split122(oracle.linearize_gpumap(m, xyz1, cov1, delta)[0])
+        for module in range(3):  # odometry / sub-mapping (mixed contexts) / global mapping
+            got = oracle.split122(recs[2 * module + level])
+            assert got["num_inliers"] == ref["num_inliers"] > 0
+            for k in ("H_tt", "H_ss", "H_ts"):
+                assert util.rel_err(got[k], ref[k]) < util.REL_TOL
+        if level == 1:
+            assert ov[0] == ov[1] == ov[2] == oracle.overlap_gpumap([m], xyz1, [delta])

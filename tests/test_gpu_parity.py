@@ -408,7 +408,7 @@ def test_kernel_generations_agree(ctx, dev, monkeypatch):
     maps0 = [gpu.GaussianVoxelMapGPU(r, ctx=ctx).insert(dev["cloud"][0]) for r in (0.25, 0.5)]
     T = dev["T_gt"]
     outs = {}
-    for name, env in (("v4_128", {"GB_KERNEL": "4", "GB_STAGE": "128"}), ("v4_64", {"GB_KERNEL": "4", "GB_STAGE": "64"}), ("v3", {"GB_KERNEL": "3"}), ("v4_big_items", {"GB_KERNEL": "4", "GB_TILE": "2048"})):
+    for name, env in (("v4_128", {"GB_KERNEL": "4", "GB_STAGE": "128"}), ("v4_64", {"GB_KERNEL": "4", "GB_STAGE": "64"}), ("v3", {"GB_KERNEL": "3"}), ("v5", {"GB_KERNEL": "5"}), ("v5_big_items", {"GB_KERNEL": "5", "GB_TILE": "2048"}), ("v4_big_items", {"GB_KERNEL": "4", "GB_TILE": "2048"})):
         for k in ("GB_KERNEL", "GB_STAGE", "GB_TILE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
@@ -418,7 +418,7 @@ def test_kernel_generations_agree(ctx, dev, monkeypatch):
         outs[name] = fs.linearize_deltas(np.stack([T, T]))
         e = fs.error_deltas(np.stack([T, T]), np.stack([T, T]))
         assert np.allclose(e, outs[name]["error"], rtol=1e-5)
-    for name in ("v4_64", "v3", "v4_big_items"):
+    for name in ("v4_64", "v3", "v5", "v5_big_items", "v4_big_items"):
         for i in range(2):
             assert outs[name][i]["num_inliers"] == outs["v4_128"][i]["num_inliers"]
             for k in ("H_tt", "H_ss", "H_ts"):
