@@ -24,7 +24,7 @@ SYMBOLS = [
     "gb_sweep_results_device", "gb_sweep_stats",
     "gb_peer_slab_create", "gb_peer_slab_export", "gb_peer_slab_connect", "gb_peer_slab_destroy", "gb_sweep_attach_peer_slab",
     "gb_peer_slab_signal_wait", "gb_peer_slab_device_ptr", "gb_peer_slab_fetch", "gb_peer_slab_fetch_async",
-    "gb_overlap", "gb_covariances", "gb_find_neighbors", "gb_voxelgrid_sampling",
+    "gb_overlap", "gb_covariances", "gb_find_neighbors", "gb_voxelgrid_sampling", "gb_preprocess_default_params", "gb_preprocess",
     "gb_deskew_pose_table", "gb_deskew",
 ]
 
@@ -35,6 +35,20 @@ GB_FACTOR_SURFACE_VALIDATION = 1
 
 class GlimB200Error(RuntimeError):
     pass
+
+
+class PreprocessParams(C.Structure):
+    """gb_preprocess_params (include/glim_b200.h)."""
+    _fields_ = [("distance_near_thresh", C.c_double), ("distance_far_thresh", C.c_double), ("use_random_grid_downsampling", C.c_int), ("downsample_resolution", C.c_double),
+                ("downsample_target", C.c_int), ("downsample_rate", C.c_double), ("seed", C.c_uint64), ("global_shutter", C.c_int), ("crop_bbox_frame", C.c_int),
+                ("crop_bbox_min", C.c_double * 3), ("crop_bbox_max", C.c_double * 3), ("T_imu_lidar", C.c_double * 16), ("enable_outlier_removal", C.c_int),
+                ("k_correspondences", C.c_int), ("estimate_covariances", C.c_int), ("k_neighbors_cov", C.c_int), ("knn_cell_size", C.c_double)]
+
+
+class Preprocessed(C.Structure):
+    """gb_preprocessed (include/glim_b200.h)."""
+    _fields_ = [("num_points", C.c_size_t), ("last_time", C.c_double), ("times", C.c_void_p), ("xyzw", C.c_void_p), ("intensities", C.c_void_p), ("neighbors", C.c_void_p),
+                ("normals4", C.c_void_p), ("cov4x4", C.c_void_p), ("cloud", C.c_void_p)]
 
 
 _lib = None
@@ -67,6 +81,8 @@ def lib():
     L.gb_cloud_download.argtypes = [vp, vp, vp]
     L.gb_cloud_destroy.argtypes = [vp]
     L.gb_cloud_device_ptrs.argtypes = [vp, vp, vp, vp, vp]
+    L.gb_preprocess_default_params.argtypes = [vp]
+    L.gb_preprocess.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.gb_hessian_blocks.argtypes = [vp, f64, vp, vp, vp, vp, vp, vp]
     L.gb_slab_row_hessian_blocks.argtypes = [vp, f64, vp, vp, vp, vp, vp, vp, vp]
     L.gb_voxelmap_build.argtypes = [vp, vp, f32, i32, i32, f64, vp]

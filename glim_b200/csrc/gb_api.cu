@@ -322,7 +322,7 @@ extern "C" gb_status gb_vgicp_factor_create(gb_ctx* ctx, const gb_voxelmap* targ
   GB_REQUIRE(target->device == ctx->device && source->device == ctx->device, "cloud / voxel map live on another device");
   gb_factor* f = new (std::nothrow) gb_factor();
   if (!f) return GB_ERR_INTERNAL;
-  f->ctx = ctx; f->target = target; f->source = source; f->flags = flags; f->single = nullptr; f->id = g_next_factor_id.fetch_add(1);
+  f->ctx = ctx; f->target = target; f->source = source; f->flags = flags; f->single = nullptr; f->inlier_frac = -1.f; f->id = g_next_factor_id.fetch_add(1);
   ctx_retain(ctx);
   *out = f;
   return GB_OK;
@@ -399,6 +399,83 @@ static int env_int(const char* name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
+// The work-item table of a sweep (descs[f].num_tiles / first_tile and the (factor, offset) list).
+//   contiguous: items of tile_size consecutive points, factor-major (drawn from the queue by the persistent warps);
+//   strided   : about one item per warp in total; factor f gets J_f items in proportion to its expected cost
+//               n_f * (1 + 1.25 r_f) (r_f = inlier fraction of its last linearization, 0.5 if unknown; a hit costs ~2.2x a
+//               miss), item j owning the 32-point rows j, j + J_f, ... of the source cloud.
+static void build_items(gb_sweep* s, FactorDesc* descs, std::vector<int2>& tiles) {
+  tiles.clear();
+  const size_t F = s->F;
+  if (!s->strided) {
+    for (size_t f = 0; f < F; f++) {
+      FactorDesc& D = descs[f];
+      D.first_tile = (int)tiles.size();
+      // a factor with no points still gets one (empty) item so that its epilogue runs and zeroes its record
+      const int nt = std::max(1, (D.n + s->tile_size - 1) / s->tile_size);
+      D.num_tiles = nt;
+      for (int t = 0; t < nt; t++) tiles.push_back(make_int2((int)f, t * s->tile_size));
+    }
+    return;
+  }
+  const double warps = (double)s->capacity * 8.0;
+  const int min_rows = std::max(1, env_int("GB_MIN_ROWS", 4));
+  std::vector<double> cost(F);
+  double tot = 0.0;
+  for (size_t f = 0; f < F; f++) {
+    const gb_factor* fa = s->factors[f];
+    const double r = (fa && fa->inlier_frac >= 0.f) ? (double)fa->inlier_frac : 0.5;
+    cost[f] = (double)descs[f].n * (1.0 + 1.25 * r) + 64.0;  // + a floor so that empty factors get their one item
+    tot += cost[f];
+  }
+  std::vector<int> J(F);
+  double budget = warps;
+  for (int iter = 0; iter < 64; iter++) {
+    long long sum = 0;
+    for (size_t f = 0; f < F; f++) {
+      const int rows = (descs[f].n + 31) / 32;
+      const int jmax = std::max(1, rows / min_rows);
+      J[f] = std::min(jmax, std::max(1, (int)(cost[f] / tot * budget + 0.5)));
+      sum += J[f];
+    }
+    if ((double)sum <= warps) break;
+    budget *= 0.95;
+  }
+  for (size_t f = 0; f < F; f++) {
+    descs[f].first_tile = (int)tiles.size();
+    descs[f].num_tiles = J[f];
+    for (int j = 0; j < J[f]; j++) tiles.push_back(make_int2((int)f, j));
+  }
+}
+
+// After results have been fetched (the stream is idle): remember every factor's inlier fraction, and -- once per strided
+// sweep -- re-size its item table from them.
+static gb_status sweep_learn_inliers(gb_sweep* s) {
+  for (size_t f = 0; f < s->F; f++) {
+    gb_factor* fa = s->factors[f];
+    if (fa && fa->source->n) fa->inlier_frac = (float)(s->h_out[f * GB_OUT_DOUBLES + 121] / (double)fa->source->n);
+  }
+  if (!s->strided || s->calibrated || s->stale) return GB_OK;
+  s->calibrated = true;
+  std::vector<int> old(s->F);
+  for (size_t f = 0; f < s->F; f++) old[f] = s->h_descs[f].num_tiles;
+  std::vector<int2> tiles;
+  build_items(s, s->h_descs, tiles);
+  bool changed = false;
+  for (size_t f = 0; f < s->F; f++) changed = changed || std::abs(old[f] - s->h_descs[f].num_tiles) * 8 > old[f];
+  if (!changed || tiles.size() > s->tiles_cap) {  // keep the old table
+    int first = 0;
+    for (size_t f = 0; f < s->F; f++) { s->h_descs[f].num_tiles = old[f]; s->h_descs[f].first_tile = first; first += old[f]; }
+    return GB_OK;
+  }
+  memcpy(s->h_tiles, tiles.data(), sizeof(int2) * tiles.size());
+  GB_CUDA(cudaMemcpyAsync(s->d_descs, s->h_descs, sizeof(FactorDesc) * s->F, cudaMemcpyHostToDevice, s->ctx->stream));
+  GB_CUDA(cudaMemcpyAsync(s->d_tiles, s->h_tiles, sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, s->ctx->stream));
+  s->num_tiles = (int)tiles.size();
+  s->grid = std::max(1, std::min((s->num_tiles + 7) / 8, s->capacity));
+  return GB_OK;
+}
+
 extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* factors, const int32_t* pair_index, gb_sweep** out) {
   GB_REQUIRE(ctx && out, "null argument");
   GB_REQUIRE(F == 0 || factors, "null factor list");
@@ -424,23 +501,30 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   s->h_pose_slot[0] = s->h_pose_slot[1] = nullptr; s->pose_ev[0] = s->pose_ev[1] = nullptr; s->pose_slot = 0;
   s->pool_d = nullptr; s->pool_d_cap = 0; s->pool_h = nullptr; s->pool_h_cap = 0;
 
-  // kernel generation and work-item size
-  { const int kv = env_int("GB_KERNEL", 4); s->kernel_version = (kv == 3 || kv == 5) ? kv : 4; }
+  // kernel generation and work-item policy
+  { const int kv = env_int("GB_KERNEL", 5); s->kernel_version = (kv == 3 || kv == 4) ? kv : 5; }
   s->stage_points = env_int("GB_STAGE", 128) == 64 ? 64 : 128;
-  const int T = s->kernel_version == 4 ? s->stage_points : 32;
   const int ctas_per_sm = (s->kernel_version == 4 && s->stage_points == 64) ? 3 : 2;
-  const int capacity = ctx->num_sms * ctas_per_sm;
-  int tile = env_int("GB_TILE", 0);
-  if (tile <= 0) {
-    // work items are per WARP: ~GB_ITEMS_PER_WARP items per warp (first one static, the rest drawn dynamically), between
-    // one stage and 2048 points each (profiles/tune_sweep_r0*.txt)
-    const uint64_t warps = (uint64_t)capacity * 8;
-    const uint64_t ipw = (uint64_t)std::max(1, env_int("GB_ITEMS_PER_WARP", s->kernel_version == 4 ? 4 : 6));
-    const uint64_t want = total_pts / (warps * ipw) + 1;
-    tile = (int)std::min<uint64_t>(2048, std::max<uint64_t>(s->kernel_version == 4 ? T : 128, want));
+  s->capacity = ctx->num_sms * ctas_per_sm;
+  const uint64_t warps = (uint64_t)s->capacity * 8;
+  // one wave of equally expensive STRIDED items when the sweep is small (an odometry frame, a single pair); contiguous items
+  // drawn from a queue otherwise
+  s->strided = (s->kernel_version == 5 && F > 0 && env_int("GB_STRIDED", 1) && total_pts <= warps * 2048) ? 1 : 0;
+  s->calibrated = false;
+  s->pipe = env_int("GB_PIPE", 0) & 3;
+  s->h_descs = nullptr; s->h_tiles = nullptr; s->tiles_cap = 0;
+  {
+    const int T = s->kernel_version == 4 ? s->stage_points : 32;
+    int tile = env_int("GB_TILE", 0);
+    if (tile <= 0) {
+      // contiguous items: ~GB_ITEMS_PER_WARP items per warp (first one static, the rest drawn dynamically), between 128 and
+      // 2048 points each (profiles/tune_sweep_r0*.txt)
+      const uint64_t ipw = (uint64_t)std::max(1, env_int("GB_ITEMS_PER_WARP", s->kernel_version == 4 ? 4 : 6));
+      const uint64_t want = total_pts / (warps * ipw) + 1;
+      tile = (int)std::min<uint64_t>(2048, std::max<uint64_t>(s->kernel_version == 4 ? T : 128, want));
+    }
+    s->tile_size = std::min(1 << 20, std::max(T, (tile + T - 1) / T * T));
   }
-  tile = std::min(1 << 20, std::max(T, (tile + T - 1) / T * T));
-  s->tile_size = tile;
 
   std::vector<FactorDesc> descs(F);
   std::vector<int2> tiles;
@@ -456,11 +540,7 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     D.pair = pair_index ? pair_index[f] : (int)f;
     s->h_pair.push_back(D.pair);
     D.flags = fa->flags;
-    D.first_tile = (int)tiles.size();
-    // a factor with no points still gets one (empty) tile so that its epilogue runs and zeroes its record
-    const int nt = std::max(1, (D.n + tile - 1) / tile);
-    D.num_tiles = nt;
-    for (int t = 0; t < nt; t++) tiles.push_back(make_int2((int)f, t * tile));
+    D.num_tiles = 1; D.first_tile = 0;
     s->point_factors += (uint64_t)D.n;
     // B_f of SURVEY 8(d): 48 B per source point, 48 B per target voxel, 16 B per bucket, pose in + record out.
     // The bucket term is charged at the SMALLEST table that could hold the voxels (16384 doubled until >= V), not at
@@ -469,8 +549,9 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     while (nb_ref < (uint64_t)fa->target->num_voxels) nb_ref *= 2;
     s->algorithmic_bytes += (uint64_t)D.n * 48 + (uint64_t)fa->target->num_voxels * 48 + nb_ref * 16 + 64 + 488;
   }
+  build_items(s, descs.data(), tiles);
   s->num_tiles = (int)tiles.size();
-  s->grid = std::max(1, std::min((s->num_tiles + 7) / 8, capacity));
+  s->grid = std::max(1, std::min((s->num_tiles + 7) / 8, s->capacity));
   // ~64 items per accumulator copy: sweeps with few factors (an odometry frame, a single pair) would otherwise
   // serialise hundreds of fp64 reductions on the same addresses
   s->acc_slots = 1;
@@ -478,10 +559,11 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
 
   if (F > 0) {
     // one device block, one pinned block -- taken from the context's pool when a retired sweep left a fitting one
-    const size_t b_desc = align_up(sizeof(FactorDesc) * F, 256), b_tiles = align_up(sizeof(int2) * tiles.size(), 256), b_pose = align_up(sizeof(double) * 16 * F, 256);
+    s->tiles_cap = std::max<size_t>(tiles.size(), s->strided ? (size_t)warps + F : 0);
+    const size_t b_desc = align_up(sizeof(FactorDesc) * F, 256), b_tiles = align_up(sizeof(int2) * s->tiles_cap, 256), b_pose = align_up(sizeof(double) * 16 * F, 256);
     const size_t b_acc = align_up(sizeof(double) * GB_ACC_STRIDE * F * s->acc_slots, 256), b_done = align_up(sizeof(unsigned) * F + 16, 256), b_out = align_up(sizeof(double) * GB_OUT_DOUBLES * F, 256);
     const size_t total = b_desc + b_tiles + 2 * b_pose + b_acc + b_done + b_out;
-    const size_t h_total = 3 * b_pose + b_out + align_up(sizeof(FactorDesc) * F, 256) + b_tiles;
+    const size_t h_total = 3 * b_pose + b_out + b_desc + b_tiles;
     gb_pool_block blk{nullptr, 0, nullptr, 0};
     if (!pool_get(ctx, total, h_total, &blk)) {
       cudaError_t e = cudaMalloc(&blk.d, total);
@@ -504,13 +586,13 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     s->d_out = (double*)d;
     char* h = (char*)blk.h;
     s->h_pose_slot[0] = (double*)h; s->h_pose_slot[1] = (double*)(h + b_pose); s->h_poses_eval = (double*)(h + 2 * b_pose); s->h_out = (double*)(h + 3 * b_pose);
-    char* h_desc = h + 3 * b_pose + b_out;
-    char* h_tiles = h_desc + align_up(sizeof(FactorDesc) * F, 256);
-    memcpy(h_desc, descs.data(), sizeof(FactorDesc) * F);
-    memcpy(h_tiles, tiles.data(), sizeof(int2) * tiles.size());
+    s->h_descs = (FactorDesc*)(h + 3 * b_pose + b_out);
+    s->h_tiles = (int2*)(h + 3 * b_pose + b_out + b_desc);
+    memcpy(s->h_descs, descs.data(), sizeof(FactorDesc) * F);
+    memcpy(s->h_tiles, tiles.data(), sizeof(int2) * tiles.size());
     cudaStream_t st = ctx->stream;
-    cudaError_t e = cudaMemcpyAsync(s->d_descs, h_desc, sizeof(FactorDesc) * F, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_tiles, h_tiles, sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(s->d_descs, s->h_descs, sizeof(FactorDesc) * F, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_tiles, s->h_tiles, sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_accum, 0, b_acc + b_done, st);
     for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&s->pose_ev[k], cudaEventDisableTiming);
     if (e != cudaSuccess) { sweep_free(s); gb_set_error("sweep setup: %s", cudaGetErrorString(e)); return GB_ERR_CUDA; }
@@ -572,7 +654,7 @@ extern "C" gb_status gb_sweep_fetch(gb_sweep* s, gb_linearized6* out) {
   GB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, sizeof(double) * GB_OUT_DOUBLES * s->F, cudaMemcpyDeviceToHost, s->ctx->stream));
   GB_CUDA(cudaStreamSynchronize(s->ctx->stream));
   memcpy(out, s->h_out, sizeof(double) * GB_OUT_DOUBLES * s->F);
-  return GB_OK;
+  return sweep_learn_inliers(s);
 }
 extern "C" gb_status gb_sweep_results_device(gb_sweep* s, void** device_ptr) {
   GB_REQUIRE(s && device_ptr, "null argument");
@@ -901,8 +983,58 @@ extern "C" gb_status gb_find_neighbors(gb_ctx* ctx, size_t n, const double* xyzw
   GB_REQUIRE(ctx, "null ctx");
   if (n == 0) return GB_OK;
   GB_REQUIRE(xyzw && neighbors && k > 0, "null argument");
+  GB_LOCK(ctx);
   GB_CUDA(cudaSetDevice(ctx->device));
+  // >= 4096 points: exact search on a pyramid of hash grids (one Morton sort, cell size 0.25 m x 4^level);
+  // GB_KNN=grid selects the round-1 single-level grid, GB_KNN=brute the tiled brute force
+  const char* mode = getenv("GB_KNN");
+  const bool pyramid = mode ? (strcmp(mode, "pyramid") == 0) : (n >= 4096);
+  if (pyramid) return gb_find_neighbors_pyramid_impl(ctx, n, xyzw, k, neighbors);
   return gb_find_neighbors_impl(ctx, n, xyzw, k, neighbors);
+}
+
+extern "C" gb_status gb_preprocess_default_params(gb_preprocess_params* p) {
+  GB_REQUIRE(p, "null params");
+  memset(p, 0, sizeof(*p));
+  p->distance_near_thresh = 0.5;      // config_preprocess.json:20
+  p->distance_far_thresh = 100.0;     // :21
+  p->use_random_grid_downsampling = 1;  // :22
+  p->downsample_resolution = 1.0;     // :23
+  p->downsample_target = 10000;       // :24
+  p->downsample_rate = 0.1;           // :25
+  p->seed = 0;
+  p->k_correspondences = 10;          // :33
+  p->estimate_covariances = 1;
+  for (int i = 0; i < 4; i++) p->T_imu_lidar[i * 5] = 1.0;
+  return GB_OK;
+}
+extern "C" gb_status gb_preprocess(gb_ctx* ctx, size_t n, const double* xyzw, const double* times, const double* intensities, const gb_preprocess_params* P, gb_preprocessed* out) {
+  GB_REQUIRE(ctx && P && out, "null argument");
+  out->num_points = 0; out->last_time = 0.0; out->cloud = nullptr;
+  GB_REQUIRE(n < (size_t)1 << 30, "too many points");
+  GB_REQUIRE(P->k_correspondences > 0, "k_correspondences must be positive");
+  GB_REQUIRE(P->k_neighbors_cov >= 0 && P->k_neighbors_cov <= P->k_correspondences, "k_neighbors_cov must be in [0, k_correspondences]");
+  GB_REQUIRE(!P->enable_outlier_removal, "statistical outlier removal is not implemented (its rule lives in the un-vendored gtsam_points)");
+  GB_REQUIRE(P->crop_bbox_frame >= 0 && P->crop_bbox_frame <= 2, "crop_bbox_frame must be 0 (off), 1 (lidar) or 2 (imu)");
+  if (n == 0) return GB_OK;
+  GB_REQUIRE(xyzw, "null points");
+  GB_LOCK(ctx);
+  GB_CUDA(cudaSetDevice(ctx->device));
+  gb_cloud* c = nullptr;
+  if (P->estimate_covariances) {
+    c = new (std::nothrow) gb_cloud();
+    if (!c) return GB_ERR_INTERNAL;
+    c->device = ctx->device; c->n = 0; c->base = nullptr; c->bytes = 0;
+    c->p0 = nullptr; c->p1 = nullptr; c->p2 = nullptr; c->normals = nullptr; c->perm = nullptr; c->inv_perm = nullptr;
+  }
+  gb_status st = gb_preprocess_impl(ctx, n, xyzw, times, intensities, P, out, c);
+  if (st == GB_OK) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);  // the cloud is complete when the call returns (it may be used from another context)
+    if (e != cudaSuccess) { gb_set_error("gb_preprocess: %s", cudaGetErrorString(e)); st = GB_ERR_CUDA; }
+  }
+  if (st != GB_OK) { if (c) { if (c->base) cudaFree(c->base); delete c; } return st; }
+  out->cloud = c;
+  return GB_OK;
 }
 extern "C" gb_status gb_voxelgrid_sampling(gb_ctx* ctx, size_t n, const double* xyzw, const double* times, const double* intensities, double resolution, double* out_xyzw, double* out_times, double* out_intensities, size_t* num_out) {
   GB_REQUIRE(ctx && num_out, "null argument");

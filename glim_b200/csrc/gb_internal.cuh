@@ -93,6 +93,7 @@ struct gb_factor {
   const gb_cloud* source;
   int flags;
   gb_sweep* single;  // lazily created 1-factor sweep
+  float inlier_frac; // inlier fraction of the last linearization (< 0: unknown) -- sizes the work items of the next sweep
   uint64_t id;       // process-wide unique
   std::vector<gb_sweep*> users;  // sweeps (of any context) that reference this factor; guarded by the registry mutex
 };
@@ -151,7 +152,14 @@ struct gb_sweep {
   PeerPush* d_peer_tables;        // [2]: one per step parity
   std::vector<int> h_pair;        // pair id per factor
   int num_tiles, tile_size, grid;   // work items, points per item, CTAs
-  int kernel_version;               // 4 = bulk-async staged kernel (default), 3 = round-1 kernel (GB_KERNEL=3)
+  int kernel_version;               // 5 = default kernel; 4 = bulk-async (TMA) staged kernel; 3 = round-1 kernel (GB_KERNEL=3/4)
+  int pipe;                         // v5 software-pipelining variant (GB_PIPE; A/B only)
+  int strided;                      // v5, about one item per warp: item j of a factor owns the rows j, j + J, ... (see k_vgicp_sweep5)
+  bool calibrated;                  // strided: the item table has been re-sized from measured inlier fractions
+  int capacity;                     // CTAs of a full grid
+  FactorDesc* h_descs;              // pinned copies (re-uploaded when the item table is re-sized)
+  int2* h_tiles;
+  size_t tiles_cap;
   int stage_points;                 // v4: points per shared-memory stage (128: 2 CTAs / SM; 64: 3 CTAs / SM)
   uint64_t point_factors, algorithmic_bytes;
   uint64_t key;           // cache key
@@ -197,6 +205,8 @@ gb_status gb_cloud_reorder_impl(gb_ctx* ctx, gb_cloud* c, const void* staged /* 
 size_t gb_cloud_reorder_scratch_bytes(size_t n, size_t staged_bytes);
 gb_status gb_voxelmap_build_impl(gb_ctx* ctx, const gb_cloud* cloud, float resolution, int init_buckets, int max_scan, double drop_rate, gb_voxelmap* out);
 gb_status gb_covariances_impl(gb_ctx* ctx, size_t n, const double* xyzw, const int32_t* neighbors, int kc, int k, double* normals4, double* cov4x4);
+gb_status gb_preprocess_impl(gb_ctx* ctx, size_t n, const double* xyzw, const double* times, const double* intensities, const gb_preprocess_params* P, gb_preprocessed* out, gb_cloud* cloud_out);
+gb_status gb_find_neighbors_pyramid_impl(gb_ctx* ctx, size_t n, const double* xyzw, int k, int32_t* neighbors);
 gb_status gb_find_neighbors_impl(gb_ctx* ctx, size_t n, const double* xyzw, int k, int32_t* neighbors);
 gb_status gb_voxelgrid_sampling_impl(gb_ctx* ctx, size_t n, const double* xyzw, const double* times, const double* intensities, double resolution, double* out_xyzw, double* out_times, double* out_intensities, size_t* num_out);
 

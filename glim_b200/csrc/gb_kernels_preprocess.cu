@@ -562,3 +562,568 @@ gb_status gb_voxelgrid_sampling_impl(gb_ctx* ctx, size_t n_, const double* xyzw,
   *num_out = (size_t)V;
   return GB_OK;
 }
+
+// =============================================================================================
+// gb_preprocess: the whole per-frame preprocess on the device, without host round trips
+//   CloudPreprocessor::preprocess_impl (src/glim/preprocess/cloud_preprocessor.cpp:92-188): downsample (voxel grid :108 or
+//   random grid :104-106) -> finite + range gate (:116-128) -> crop box (:143-162) -> time order (:135-136) ->
+//   global shutter (:138-140) -> k-NN (:182-183, :190-221)
+//   + CloudCovarianceEstimation::estimate (src/glim/common/cloud_covariance_estimation.cpp:43-122; called on the preprocessed
+//   frame at src/glim/odometry/odometry_estimation_imu.cpp:322-328) + PointCloudGPU::clone (odometry_estimation_gpu.cpp:96):
+//   the fp32 planes of the gb_cloud are written straight from the covariance kernel's registers.
+// One H2D of the raw scan, no host synchronisation until the point count is needed to size the cloud, optional D2H of
+// the host-side products (PreprocessedFrame fields, covariances, normals).
+// =============================================================================================
+namespace {
+
+// ---- Morton keys: one sort serves a whole pyramid of grids (cell size h0 * 4^level: a coarser cell is key >> 6 level) ----
+__device__ __forceinline__ unsigned long long spread21(unsigned long long x) {
+  x &= 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+__device__ __forceinline__ unsigned long long morton3(unsigned x, unsigned y, unsigned z) { return (spread21(x) << 2) | (spread21(y) << 1) | spread21(z); }
+
+constexpr int kMlLevels = 4;
+constexpr double kMlOffset = 1048576.0;  // 2^20: coordinates are offset to [0, 2^21)
+struct MlCell { unsigned long long key; int start; int pad; };
+constexpr unsigned long long kMlEmpty = ~0ull;
+
+__device__ __forceinline__ unsigned ml_hash(unsigned long long key, unsigned mask) { return (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 32) & mask; }
+
+// valid = device count of leading valid points (points [0, *valid) are considered; the rest get the invalid key)
+__global__ void k_ml_keys(int n, const int* __restrict__ valid, const double4* __restrict__ pts, double inv_h0, unsigned long long* __restrict__ keys, int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long key = kMlEmpty;
+  if (i < *valid) {
+    const double4 p = pts[i];
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      const double fx = floor(p.x * inv_h0) + kMlOffset, fy = floor(p.y * inv_h0) + kMlOffset, fz = floor(p.z * inv_h0) + kMlOffset;
+      if (fx >= 0.0 && fx < 2097152.0 && fy >= 0.0 && fy < 2097152.0 && fz >= 0.0 && fz < 2097152.0) key = morton3((unsigned)fx, (unsigned)fy, (unsigned)fz);
+    }
+  }
+  keys[i] = key;
+  idx[i] = i;
+}
+__global__ void k_ml_gather(int n, const unsigned long long* __restrict__ keys_s, const int* __restrict__ idx_s, const double4* __restrict__ pts, double4* __restrict__ pts_s) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n && keys_s[s] != kMlEmpty) pts_s[s] = pts[idx_s[s]];
+}
+// every first point of a cell (at every level) registers the cell's start in that level's hash table
+__global__ void k_ml_cells(int n, const unsigned long long* __restrict__ keys_s, MlCell* __restrict__ tables, unsigned table_size) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const unsigned long long key = keys_s[s];
+  if (key == kMlEmpty) return;
+  const unsigned long long prev = s > 0 ? keys_s[s - 1] : kMlEmpty;
+#pragma unroll
+  for (int l = 0; l < kMlLevels; l++) {
+    const unsigned long long kl = key >> (6 * l);
+    if (s > 0 && (prev >> (6 * l)) == kl) continue;
+    MlCell* tab = tables + (size_t)l * table_size;
+    unsigned slot = ml_hash(kl, table_size - 1);
+    while (true) {
+      const unsigned long long old = atomicCAS(&tab[slot].key, kMlEmpty, kl);
+      if (old == kMlEmpty) { tab[slot].start = s; break; }
+      slot = (slot + 1) & (table_size - 1);
+    }
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void knn_insert(double (&bd)[K], int (&bi)[K], int& cnt, double d, int j) {
+  if (d < bd[K - 1] || (d == bd[K - 1] && j < bi[K - 1])) {
+    double cd = d;
+    int ci = j;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (cd < bd[k] || (cd == bd[k] && ci < bi[k])) {
+        const double td = bd[k]; const int ti = bi[k];
+        bd[k] = cd; bi[k] = ci; cd = td; ci = ti;
+      }
+    }
+    cnt++;
+  }
+}
+
+// Exact k-NN on the pyramid: a query searches the 3x3x3 block of cells around it at the finest level; every unseen point is
+// then at least (1 + min(u, 1 - u)) * h away (u = position inside its cell), so the answer is complete as soon as the k-th
+// best distance is within that bound.  Otherwise the query moves one level up (4x larger cells); after the coarsest level it
+// scans all points.  Same un-contracted fp64 distance and (distance, index) tie rule as the brute-force kernel and the oracle.
+template <int K>
+__global__ void __launch_bounds__(128) k_knn_pyramid(int n, const double4* __restrict__ pts_s, const unsigned long long* __restrict__ keys_s, const int* __restrict__ idx_s,
+                                                     const MlCell* __restrict__ tables, unsigned table_size, double inv_h0, double h0, int* __restrict__ neighbors) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const unsigned long long key = keys_s[t];
+  if (key == kMlEmpty) return;  // not a point of the frame (or a non-finite one: the caller pre-filled its row with itself)
+  const int self = idx_s[t];
+  const double4 p = pts_s[t];
+  double bd[K];
+  int bi[K];
+  int cnt = 0;
+  bool complete = false;
+  const double px = p.x * inv_h0 + kMlOffset, py = p.y * inv_h0 + kMlOffset, pz = p.z * inv_h0 + kMlOffset;
+  double scale = 1.0, h = h0;
+  for (int l = 0; l < kMlLevels && !complete; l++, scale *= 0.25, h *= 4.0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) { bd[k] = 1e300; bi[k] = 0x7fffffff; }
+    cnt = 0;
+    const double qx = px * scale, qy = py * scale, qz = pz * scale;
+    const double fx = floor(qx), fy = floor(qy), fz = floor(qz);
+    const int cx = (int)fx, cy = (int)fy, cz = (int)fz;
+    const int cmax = (1 << (21 - 2 * l)) - 1;
+    const MlCell* tab = tables + (size_t)l * table_size;
+    for (int dx = -1; dx <= 1; dx++) {
+      const int x = cx + dx;
+      if (x < 0 || x > cmax) continue;
+      for (int dy = -1; dy <= 1; dy++) {
+        const int y = cy + dy;
+        if (y < 0 || y > cmax) continue;
+        for (int dz = -1; dz <= 1; dz++) {
+          const int z = cz + dz;
+          if (z < 0 || z > cmax) continue;
+          const unsigned long long kl = morton3((unsigned)x, (unsigned)y, (unsigned)z);
+          unsigned slot = ml_hash(kl, table_size - 1);
+          int start = -1;
+          while (true) {
+            const unsigned long long tk = tab[slot].key;
+            if (tk == kl) { start = tab[slot].start; break; }
+            if (tk == kMlEmpty) break;
+            slot = (slot + 1) & (table_size - 1);
+          }
+          if (start < 0) continue;
+          for (int s = start; s < n; s++) {
+            const unsigned long long ks = __ldg(&keys_s[s]);
+            if (ks == kMlEmpty || (ks >> (6 * l)) != kl) break;
+            const double4 q = pts_s[s];
+            const double ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+            const double d = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+            knn_insert<K>(bd, bi, cnt, d, __ldg(&idx_s[s]));
+          }
+        }
+      }
+    }
+    if (cnt >= K) {
+      const double ux = qx - fx, uy = qy - fy, uz = qz - fz;
+      const double m = 1.0 + fmin(fmin(fmin(ux, 1.0 - ux), fmin(uy, 1.0 - uy)), fmin(uz, 1.0 - uz));
+      const double bound = m * h * (1.0 - 1e-12);
+      if (bd[K - 1] <= bound * bound) complete = true;
+    }
+  }
+  if (!complete) {  // isolated point: exact scan of all points
+#pragma unroll
+    for (int k = 0; k < K; k++) { bd[k] = 1e300; bi[k] = 0x7fffffff; }
+    cnt = 0;
+    for (int s = 0; s < n; s++) {
+      if (__ldg(&keys_s[s]) == kMlEmpty) break;  // invalid keys sort last
+      const double4 q = pts_s[s];
+      const double ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+      const double d = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+      knn_insert<K>(bd, bi, cnt, d, __ldg(&idx_s[s]));
+    }
+  }
+  const int found = min(cnt, K);
+#pragma unroll
+  for (int k = 0; k < K; k++) neighbors[(size_t)self * K + k] = k < found ? bi[k] : self;
+}
+__global__ void k_fill_self(int n, int k, int* __restrict__ neighbors) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < (size_t)n * k) neighbors[e] = (int)(e / k);
+}
+
+// ---- downsampling, filtering, time order ----
+// random grid (gtsam_points::randomgrid_sampling, cloud_preprocessor.cpp:104-106): every voxel keeps at most
+// ppv = ceil(rate * N / V) of its points.  Which ones is a draw from std::mt19937 in the reference (not reproducible, SURVEY
+// C.2); here it is the ppv points with the smallest hash(seed, index) -- a fixed pseudo-random choice the oracle shares.
+__device__ __forceinline__ unsigned long long rg_hash(unsigned long long seed, unsigned i) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1u);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void k_randomgrid_select(int n, const int* __restrict__ num_voxels, const int* __restrict__ starts, const int* __restrict__ idx_s, double rate, unsigned long long seed, int* __restrict__ keep) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int V = *num_voxels;
+  if (v >= V) return;
+  const int ppv = max(1, (int)ceil(rate * (double)n / (double)V));
+  const int b = starts[v], e = starts[v + 1];
+  if (e - b <= ppv) {
+    for (int s = b; s < e; s++) keep[idx_s[s]] = 1;
+    return;
+  }
+  // the ppv smallest hashes: threshold selection by repeated minimum (ppv is small: 1-4 at GLIM's settings)
+  unsigned long long last = 0;
+  int last_idx = -1;
+  for (int r = 0; r < ppv; r++) {
+    unsigned long long best = ~0ull;
+    int best_i = -1;
+    for (int s = b; s < e; s++) {
+      const int i = idx_s[s];
+      const unsigned long long hsh = rg_hash(seed, (unsigned)i);
+      const bool after = (r == 0) || hsh > last || (hsh == last && i > last_idx);
+      if (after && (hsh < best || (hsh == best && i < best_i))) { best = hsh; best_i = i; }
+    }
+    if (best_i < 0) break;
+    keep[best_i] = 1;
+    last = best; last_idx = best_i;
+  }
+}
+
+__global__ void k_rg_hash_keys(int n, const int* __restrict__ keep, unsigned long long seed, unsigned long long* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = keep[i] ? rg_hash(seed, (unsigned)i) : ~0ull;
+}
+__global__ void k_rg_cap(int n, int cap, const unsigned long long* __restrict__ sorted, unsigned long long seed, int* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && keep[i] && rg_hash(seed, (unsigned)i) > sorted[cap - 1]) keep[i] = 0;
+}
+
+struct FrameFilter {
+  double near2, far2;
+  int crop;  // 0 none, 1 box given in the lidar frame, 2 box given in the IMU frame (p_imu = T * p_lidar)
+  double bmin[3], bmax[3];
+  double T[12];  // rows of T_imu_lidar (3x4)
+  int global_shutter;
+};
+// key = order-preserving bits of the time for the points that pass the gates, ~0 otherwise (sorted to the end, stable)
+__global__ void k_filter_time_keys(int n_upper, const int* __restrict__ count_in, const int* __restrict__ keep, const double4* __restrict__ pts, const double* __restrict__ times, FrameFilter f,
+                                   unsigned long long* __restrict__ keys, int* __restrict__ idx, int* __restrict__ count_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int ok = 0;
+  if (i < n_upper) {
+    unsigned long long key = ~0ull;
+    if (i < *count_in && (!keep || keep[i])) {
+      const double4 p = pts[i];
+      const bool finite = isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(p.w);          // :123 allFinite
+      const double sq = __dadd_rn(__dadd_rn(__dmul_rn(p.x, p.x), __dmul_rn(p.y, p.y)), __dmul_rn(p.z, p.z));  // :124
+      bool pass = finite && sq > f.near2 && sq < f.far2;                                             // :125
+      if (pass && f.crop) {                                                                            // :143-162
+        double x = p.x, y = p.y, z = p.z;
+        if (f.crop == 2) {
+          x = f.T[0] * p.x + f.T[1] * p.y + f.T[2] * p.z + f.T[3];
+          y = f.T[4] * p.x + f.T[5] * p.y + f.T[6] * p.z + f.T[7];
+          z = f.T[8] * p.x + f.T[9] * p.y + f.T[10] * p.z + f.T[11];
+        }
+        const bool inside = x >= f.bmin[0] && x <= f.bmax[0] && y >= f.bmin[1] && y <= f.bmax[1] && z >= f.bmin[2] && z <= f.bmax[2];
+        pass = !inside;
+      }
+      if (pass) {
+        const double t = times ? times[i] : 0.0;
+        unsigned long long b = (unsigned long long)__double_as_longlong(t);
+        b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);  // total order of doubles as unsigned
+        key = b == ~0ull ? b - 1 : b;
+        ok = 1;
+      }
+    }
+    keys[i] = key;
+    idx[i] = i;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count_out, __popc(m));
+}
+__global__ void k_gather_frame(int n_upper, const int* __restrict__ count, const int* __restrict__ idx_s, const double4* __restrict__ pts, const double* __restrict__ times, const double* __restrict__ intens, int global_shutter,
+                               double4* __restrict__ o_pts, double* __restrict__ o_times, double* __restrict__ o_intens) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_upper || s >= *count) return;
+  const int i = idx_s[s];
+  o_pts[s] = pts[i];
+  if (o_times) o_times[s] = (times && !global_shutter) ? times[i] : 0.0;
+  if (intens && o_intens) o_intens[s] = intens[i];
+}
+__global__ void k_grid_means_counted(const int* __restrict__ num_voxels, const int* __restrict__ starts, const int* __restrict__ idx, const double4* __restrict__ pts, const double* __restrict__ times, const double* __restrict__ intens,
+                                     double4* __restrict__ out_pts, double* __restrict__ out_times, double* __restrict__ out_intens) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= *num_voxels) return;
+  const int b = starts[v], e = starts[v + 1];
+  double sx = 0, sy = 0, sz = 0, sw = 0, st = 0, si = 0;
+  for (int s = b; s < e; s++) {  // same sums in the same order as k_grid_means / the oracle
+    const int i = idx[s];
+    const double4 p = pts[i];
+    sx += p.x; sy += p.y; sz += p.z; sw += p.w;
+    if (times) st += times[i];
+    if (intens) si += intens[i];
+  }
+  const int cnt = e - b;
+  out_pts[v] = make_double4(sx / cnt, sy / cnt, sz / cnt, sw / cnt);
+  if (times) out_times[v] = st / cnt;
+  if (intens) out_intens[v] = si / cnt;
+}
+__global__ void k_set_int(int* p, int v) { *p = v; }
+__global__ void k_copy_last_pos(int n, const int* __restrict__ pos, int* __restrict__ out) { *out = n > 0 ? pos[n - 1] : 0; }
+
+// covariance estimation (same arithmetic as k_covariances) writing the fp64 host-layout outputs AND the fp32 planes of the
+// device cloud in the caller's point order (the Morton reorder of gb_cloud_upload follows)
+__global__ void __launch_bounds__(128) k_covariances_planes(int n_upper, const int* __restrict__ count, const double4* __restrict__ pts, const int* __restrict__ neighbors, int kc, int k,
+                                                            double4* __restrict__ normals, double* __restrict__ covs, float4* __restrict__ s0, float4* __restrict__ s1, float* __restrict__ s2, float4* __restrict__ s3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_upper || i >= *count) return;
+  double S[4] = {0, 0, 0, 0};
+  double X[16];
+  for (int e = 0; e < 16; e++) X[e] = 0.0;
+  const size_t begin = (size_t)kc * (size_t)i;
+  for (int j = 0; j < k; j++) {
+    const double4 q = pts[neighbors[begin + j]];
+    const double p[4] = {q.x, q.y, q.z, q.w};
+    for (int r = 0; r < 4; r++) S[r] += p[r];
+    for (int c = 0; c < 4; c++)
+      for (int r = 0; r < 4; r++) X[c * 4 + r] += p[r] * p[c];
+  }
+  double mean[4], A[9];
+  for (int r = 0; r < 4; r++) mean[r] = S[r] / k;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) A[r * 3 + c] = (X[c * 4 + r] - mean[r] * S[c]) / k;
+  double evals[3], V[9];
+  eigen_sym3_direct(A, evals, V);
+  const double values[3] = {1e-3, 1.0, 1.0};
+  double C[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) {
+      double s = 0;
+      for (int e = 0; e < 3; e++) s += V[r * 3 + e] * values[e] * V[c * 3 + e];
+      C[r * 3 + c] = s;
+    }
+  const double4 p = pts[i];
+  double nx = V[0], ny = V[3], nz = V[6];
+  if (p.x * nx + p.y * ny + p.z * nz > 0.0) { nx = -nx; ny = -ny; nz = -nz; }
+  if (normals) normals[i] = make_double4(nx, ny, nz, 0.0);
+  if (covs) {
+    double* Co = covs + 16 * (size_t)i;
+    for (int e = 0; e < 16; e++) Co[e] = 0.0;
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) Co[c * 4 + r] = C[r * 3 + c];
+  }
+  // the host cast of PointCloudGPU::clone (fp64 -> fp32), upper triangle as gb_cloud_upload reads it from the column-major 4x4
+  s0[i] = make_float4((float)p.x, (float)p.y, (float)p.z, (float)C[0]);
+  s1[i] = make_float4((float)C[1], (float)C[2], (float)C[4], (float)C[5]);
+  s2[i] = (float)C[8];
+  s3[i] = make_float4((float)nx, (float)ny, (float)nz, 0.f);
+}
+
+template <int K>
+static void launch_knn_pyramid(int n, const double4* pts_s, const unsigned long long* keys_s, const int* idx_s, const MlCell* tables, unsigned ts, double inv_h0, double h0, int* nb, cudaStream_t st) {
+  k_knn_pyramid<K><<<(n + 127) / 128, 128, 0, st>>>(n, pts_s, keys_s, idx_s, tables, ts, inv_h0, h0, nb);
+}
+
+}  // namespace
+
+// scratch carving
+struct Carver {
+  char* base; size_t off;
+  template <typename T> T* take(size_t count) { T* p = (T*)(base + off); off += align_up(sizeof(T) * count, 256); return p; }
+};
+
+// exact k-NN of the first *d_count points of d_pts (device resident); neighbors[i * k + j]
+static gb_status knn_device(gb_ctx* ctx, int n, const int* d_count, const double4* d_pts, int k, double h0, int* d_nb, Carver& cv, size_t cub_b, void* d_cub) {
+  cudaStream_t st = ctx->stream;
+  unsigned ts = 1024;
+  while (ts < 2u * (unsigned)n) ts <<= 1;
+  unsigned long long* keys = cv.take<unsigned long long>(n);
+  unsigned long long* keys_s = cv.take<unsigned long long>(n);
+  int* idx = cv.take<int>(n);
+  int* idx_s = cv.take<int>(n);
+  double4* pts_s = cv.take<double4>(n);
+  MlCell* tables = cv.take<MlCell>((size_t)kMlLevels * ts);
+  const int tb = 256, gb = (n + tb - 1) / tb;
+  k_fill_self<<<(int)(((size_t)n * k + 255) / 256), 256, 0, st>>>(n, k, d_nb);
+  k_ml_keys<<<gb, tb, 0, st>>>(n, d_count, d_pts, 1.0 / h0, keys, idx);
+  size_t tmp = cub_b;
+  GB_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, tmp, keys, keys_s, idx, idx_s, n, 0, 64, st));
+  k_ml_gather<<<gb, tb, 0, st>>>(n, keys_s, idx_s, d_pts, pts_s);
+  GB_CUDA(cudaMemsetAsync(tables, 0xff, sizeof(MlCell) * (size_t)kMlLevels * ts, st));
+  k_ml_cells<<<gb, tb, 0, st>>>(n, keys_s, tables, ts);
+  switch (k) {
+#define GB_KNN_CASE(K) case K: launch_knn_pyramid<K>(n, pts_s, keys_s, idx_s, tables, ts, 1.0 / h0, h0, d_nb, st); break;
+    GB_KNN_CASE(1) GB_KNN_CASE(2) GB_KNN_CASE(3) GB_KNN_CASE(4) GB_KNN_CASE(5) GB_KNN_CASE(6) GB_KNN_CASE(7) GB_KNN_CASE(8)
+    GB_KNN_CASE(9) GB_KNN_CASE(10) GB_KNN_CASE(12) GB_KNN_CASE(15) GB_KNN_CASE(16) GB_KNN_CASE(20) GB_KNN_CASE(24) GB_KNN_CASE(32)
+#undef GB_KNN_CASE
+    default:
+      gb_set_error("k = %d is not an instantiated neighbour count (1-10, 12, 15, 16, 20, 24, 32)", k);
+      return GB_ERR_INVALID_ARGUMENT;
+  }
+  GB_CUDA(cudaGetLastError());
+  ctx->launches += 6;
+  return GB_OK;
+}
+
+gb_status gb_preprocess_impl(gb_ctx* ctx, size_t n_, const double* xyzw, const double* times, const double* intensities, const gb_preprocess_params* P, gb_preprocessed* out, gb_cloud* cloud_out) {
+  const int n = (int)n_;
+  cudaStream_t st = ctx->stream;
+  const int k = P->k_correspondences;
+  size_t cub_sort = 0, cub_scan = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_sort, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, n, 0, 64, st);
+  cub::DeviceScan::InclusiveSum(nullptr, cub_scan, (int*)nullptr, (int*)nullptr, n, st);
+  size_t cub_keys = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, cub_keys, (unsigned long long*)nullptr, (unsigned long long*)nullptr, n, 0, 64, st);
+  const size_t cub_b = align_up(std::max(std::max(cub_sort, cub_scan), cub_keys), 256);
+  unsigned ts = 1024;
+  while (ts < 2u * (unsigned)n) ts <<= 1;
+  const size_t N = (size_t)n;
+  const size_t planes = 2 * align_up(16 * N, 256) + align_up(4 * N, 256) + align_up(16 * N, 256);
+  const size_t total = cub_b + 256 /*counters*/ + 3 * align_up(32 * N, 256) /*raw, ds, frame pts*/ + 6 * align_up(8 * N, 256) /*times, intens x3*/ + 4 * align_up(8 * N, 256) /*keys x2 (+2 knn)*/
+                       + 8 * align_up(4 * (N + 1), 256) /*idx, flags, pos, starts, keep ...*/ + align_up(4 * N * (size_t)k, 256) + align_up(32 * N, 256) /*normals*/ + align_up(128 * N, 256) /*covs*/
+                       + align_up(32 * N, 256) /*knn pts_s*/ + align_up(sizeof(MlCell) * (size_t)kMlLevels * ts, 256) + gb_cloud_reorder_scratch_bytes(N, planes) + 4096;
+  char* base = nullptr;
+  GB_CHECK(gb_ctx_scratch(ctx, total, (void**)&base));
+  Carver cv{base, 0};
+  // the staged planes + the reorder's temporaries come first (gb_cloud_reorder_impl expects its temporaries behind the planes)
+  char* staged = cv.take<char>(gb_cloud_reorder_scratch_bytes(N, planes));
+  void* d_cub = cv.take<char>(cub_b);
+  int* d_cnt = cv.take<int>(64);  // [0] raw n, [1] after downsampling, [2] frame points, [3] voxels
+  double4* d_raw = cv.take<double4>(N);
+  double* d_t = cv.take<double>(N);
+  double* d_i = cv.take<double>(N);
+  double4* d_ds = cv.take<double4>(N);
+  double* d_dst = cv.take<double>(N);
+  double* d_dsi = cv.take<double>(N);
+  double4* d_fr = cv.take<double4>(N);
+  double* d_frt = cv.take<double>(N);
+  double* d_fri = cv.take<double>(N);
+  unsigned long long* d_keys = cv.take<unsigned long long>(N);
+  unsigned long long* d_keys_s = cv.take<unsigned long long>(N);
+  int* d_idx = cv.take<int>(N + 1);
+  int* d_idx_s = cv.take<int>(N + 1);
+  int* d_flags = cv.take<int>(N + 1);
+  int* d_pos = cv.take<int>(N + 1);
+  int* d_starts = cv.take<int>(N + 1);
+  int* d_keep = cv.take<int>(N + 1);
+  int* d_nb = cv.take<int>(N * (size_t)k);
+  double4* d_nrm = cv.take<double4>(N);
+  double* d_cov = cv.take<double>(16 * N);
+  const int tb = 256, gb = (n + tb - 1) / tb;
+
+  GB_CUDA(cudaMemcpyAsync(d_raw, xyzw, sizeof(double4) * N, cudaMemcpyHostToDevice, st));
+  if (times) GB_CUDA(cudaMemcpyAsync(d_t, times, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+  if (intensities) GB_CUDA(cudaMemcpyAsync(d_i, intensities, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaMemsetAsync(d_cnt, 0, 256, st));
+  k_set_int<<<1, 1, 0, st>>>(d_cnt + 0, n);
+
+  // ---- downsampling ----
+  const double4* cur_pts = d_raw;
+  const double* cur_t = times ? d_t : nullptr;
+  const double* cur_i = intensities ? d_i : nullptr;
+  const int* cur_cnt = d_cnt + 0;
+  const int* keep = nullptr;
+  if (P->downsample_resolution > 0.0) {
+    k_grid_keys<<<gb, tb, 0, st>>>(n, d_raw, 1.0 / P->downsample_resolution, d_keys, d_idx);
+    size_t tmp = cub_b;
+    GB_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, tmp, d_keys, d_keys_s, d_idx, d_idx_s, n, 0, 64, st));
+    k_grid_flags<<<gb, tb, 0, st>>>(n, d_keys_s, d_flags);
+    tmp = cub_b;
+    GB_CUDA(cub::DeviceScan::InclusiveSum(d_cub, tmp, d_flags, d_pos, n, st));
+    k_copy_last_pos<<<1, 1, 0, st>>>(n, d_pos, d_cnt + 3);  // V
+    k_grid_starts<<<gb, tb, 0, st>>>(n, d_keys_s, d_flags, d_pos, d_starts);
+    ctx->launches += 5;
+    if (P->use_random_grid_downsampling) {
+      const double rate = P->downsample_target > 0 ? (double)P->downsample_target / (double)n : P->downsample_rate;  // :105
+      if (rate < 0.99) {
+        GB_CUDA(cudaMemsetAsync(d_keep, 0, sizeof(int) * N, st));
+        k_randomgrid_select<<<gb, tb, 0, st>>>(n, d_cnt + 3, d_starts, d_idx_s, rate, P->seed, d_keep);
+        const int cap = (int)((double)n * rate * 1.2);
+        if (cap > 0 && cap < n) {  // thin the survivors to 1.2 * rate * N: the smallest hashes stay
+          k_rg_hash_keys<<<gb, tb, 0, st>>>(n, d_keep, P->seed, d_keys);
+          size_t tmp2 = cub_b;
+          GB_CUDA(cub::DeviceRadixSort::SortKeys(d_cub, tmp2, d_keys, d_keys_s, n, 0, 64, st));
+          k_rg_cap<<<gb, tb, 0, st>>>(n, cap, d_keys_s, P->seed, d_keep);
+          ctx->launches += 3;
+        }
+        ctx->launches++;
+        keep = d_keep;  // original order is kept; the gates below drop the rest
+      }
+    } else {
+      k_grid_means_counted<<<(n + 127) / 128, 128, 0, st>>>(d_cnt + 3, d_starts, d_idx_s, d_raw, cur_t, cur_i, d_ds, d_dst, d_dsi);
+      ctx->launches++;
+      cur_pts = d_ds; cur_t = times ? d_dst : nullptr; cur_i = intensities ? d_dsi : nullptr; cur_cnt = d_cnt + 3;
+    }
+  }
+  // ---- gates + time order (one stable sort: rejected points sort to the end) ----
+  FrameFilter ff;
+  ff.near2 = P->distance_near_thresh * P->distance_near_thresh;
+  ff.far2 = P->distance_far_thresh * P->distance_far_thresh;
+  ff.crop = P->crop_bbox_frame;
+  for (int a = 0; a < 3; a++) { ff.bmin[a] = P->crop_bbox_min[a]; ff.bmax[a] = P->crop_bbox_max[a]; }
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) ff.T[r * 4 + c] = P->T_imu_lidar[c * 4 + r];
+  ff.global_shutter = P->global_shutter;
+  k_filter_time_keys<<<gb, tb, 0, st>>>(n, cur_cnt, keep, cur_pts, cur_t, ff, d_keys, d_idx, d_cnt + 2);
+  {
+    size_t tmp = cub_b;
+    GB_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, tmp, d_keys, d_keys_s, d_idx, d_idx_s, n, 0, 64, st));
+  }
+  k_gather_frame<<<gb, tb, 0, st>>>(n, d_cnt + 2, d_idx_s, cur_pts, cur_t, cur_i, P->global_shutter, d_fr, d_frt, d_fri);
+  ctx->launches += 3;
+  // ---- k-NN ----
+  GB_CHECK(knn_device(ctx, n, d_cnt + 2, d_fr, k, P->knn_cell_size > 0.0 ? P->knn_cell_size : 0.25, d_nb, cv, cub_b, d_cub));
+  // ---- the frame's point count (the one host synchronisation before the results) ----
+  int M = 0;
+  GB_CUDA(cudaMemcpyAsync(&M, d_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  out->num_points = (size_t)M;
+  // ---- covariances, written straight into the staged fp32 planes of the cloud (PointCloudGPU::clone on the device) ----
+  if (P->estimate_covariances && M > 0) {
+    const size_t c0 = align_up(16 * (size_t)M, 256), c2 = align_up(4 * (size_t)M, 256);
+    float4* s0 = (float4*)staged;
+    float4* s1 = (float4*)(staged + c0);
+    float* s2 = (float*)(staged + 2 * c0);
+    float4* s3 = (float4*)(staged + 2 * c0 + c2);
+    k_covariances_planes<<<(M + 127) / 128, 128, 0, st>>>(M, d_cnt + 2, d_fr, d_nb, k, P->k_neighbors_cov > 0 ? P->k_neighbors_cov : k, d_nrm, d_cov, s0, s1, s2, s3);
+    GB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    if (cloud_out) {
+      const size_t ctotal = 3 * c0 + c2;
+      const size_t bperm = align_up(sizeof(int) * (size_t)M, 256);
+      cloud_out->n = (size_t)M;
+      GB_CUDA(cudaMalloc(&cloud_out->base, ctotal + 2 * bperm));
+      cloud_out->bytes = ctotal + 2 * bperm;
+      char* d = (char*)cloud_out->base;
+      cloud_out->p0 = (float4*)d; cloud_out->p1 = (float4*)(d + c0); cloud_out->p2 = (float*)(d + 2 * c0); cloud_out->normals = (float4*)(d + 2 * c0 + c2);
+      cloud_out->perm = (int*)(d + ctotal); cloud_out->inv_perm = (int*)(d + ctotal + bperm);
+      GB_CHECK(gb_cloud_reorder_impl(ctx, cloud_out, staged, c0, c0, c2, c0));
+    }
+  }
+  // ---- host products ----
+  if (M > 0) {
+    if (out->xyzw) GB_CUDA(cudaMemcpyAsync(out->xyzw, d_fr, sizeof(double4) * (size_t)M, cudaMemcpyDeviceToHost, st));
+    if (out->times) GB_CUDA(cudaMemcpyAsync(out->times, d_frt, sizeof(double) * (size_t)M, cudaMemcpyDeviceToHost, st));
+    if (out->intensities && intensities) GB_CUDA(cudaMemcpyAsync(out->intensities, d_fri, sizeof(double) * (size_t)M, cudaMemcpyDeviceToHost, st));
+    if (out->neighbors) GB_CUDA(cudaMemcpyAsync(out->neighbors, d_nb, sizeof(int) * (size_t)M * k, cudaMemcpyDeviceToHost, st));
+    if (P->estimate_covariances && out->normals4) GB_CUDA(cudaMemcpyAsync(out->normals4, d_nrm, sizeof(double4) * (size_t)M, cudaMemcpyDeviceToHost, st));
+    if (P->estimate_covariances && out->cov4x4) GB_CUDA(cudaMemcpyAsync(out->cov4x4, d_cov, sizeof(double) * 16 * (size_t)M, cudaMemcpyDeviceToHost, st));
+    double last_t = 0.0;
+    GB_CUDA(cudaMemcpyAsync(&last_t, d_frt + (M - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    out->last_time = last_t;
+  } else {
+    out->last_time = 0.0;
+  }
+  return GB_OK;
+}
+
+// gb_find_neighbors on the pyramid (host arrays in / out; the device-resident entry is inside gb_preprocess)
+gb_status gb_find_neighbors_pyramid_impl(gb_ctx* ctx, size_t n_, const double* xyzw, int k, int32_t* neighbors) {
+  const int n = (int)n_;
+  cudaStream_t st = ctx->stream;
+  size_t cub_sort = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_sort, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, n, 0, 64, st);
+  const size_t cub_b = align_up(cub_sort, 256), N = (size_t)n;
+  unsigned ts = 1024;
+  while (ts < 2u * (unsigned)n) ts <<= 1;
+  const size_t total = cub_b + 256 + 2 * align_up(32 * N, 256) + 2 * align_up(8 * N, 256) + 2 * align_up(4 * N, 256) + align_up(4 * N * (size_t)k, 256) + align_up(sizeof(MlCell) * (size_t)kMlLevels * ts, 256) + 4096;
+  char* base = nullptr;
+  GB_CHECK(gb_ctx_scratch(ctx, total, (void**)&base));
+  Carver cv{base, 0};
+  void* d_cub = cv.take<char>(cub_b);
+  int* d_cnt = cv.take<int>(64);
+  double4* d_pts = cv.take<double4>(N);
+  int* d_nb = cv.take<int>(N * (size_t)k);
+  GB_CUDA(cudaMemcpyAsync(d_pts, xyzw, sizeof(double4) * N, cudaMemcpyHostToDevice, st));
+  k_set_int<<<1, 1, 0, st>>>(d_cnt, n);
+  GB_CHECK(knn_device(ctx, n, d_cnt, d_pts, k, 0.25, d_nb, cv, cub_b, d_cub));
+  GB_CUDA(cudaMemcpyAsync(neighbors, d_nb, sizeof(int) * N * (size_t)k, cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  return GB_OK;
+}

@@ -745,21 +745,29 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep3(
 }
 
 // =============================================================================================
-// k_vgicp_sweep5 -- register-staged like v3 (no large shared-memory carve-out, L1 stays big), with the per-item latency
-// chain cut: descriptor / pose cache in shared memory for small factor sets, one-item look-ahead of the work queue,
-// software-pipelined lookup (the next group's points are loaded while the current group's buckets are in flight),
-// lazily published release tickets (no __threadfence, no L1 flush per item).  GB_KERNEL=5.
+// k_vgicp_sweep5 (default) -- register-staged like v3 (no large shared-memory carve-out: L1 stays big), with the per-item
+// latency chain cut and the one-wave regime balanced:
+//   * descriptor / fp32-pose cache in shared memory for small factor sets (an odometry graph), one-item look-ahead of the
+//     work queue, lazily published release tickets (atom.release: no __threadfence, no L1 flush per item);
+//   * software-pipelined lookup (the next group's points are loaded while the current group's buckets are in flight) and
+//     software-pipelined derivative pass (the lane's next hit -- 36-byte point + 48-byte voxel record -- is in flight
+//     while the current one is processed);
+//   * STRIDED items for sweeps of about one item per warp (odometry, single pair): item j of a factor with J items owns
+//     the 32-point rows j, j + J, j + 2J, ... of the source cloud, so every item of a factor samples the whole (Morton-
+//     ordered) cloud and sees the same inlier rate; the host sizes J per factor from the factor's last inlier fraction
+//     (a hit costs ~2.2x a miss).  One wave of equally expensive items instead of a tail of all-inlier items.
 // =============================================================================================
-template <int MODE, bool PEER>
+template <int MODE, bool PEER, int PIPE>
 __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep5(
   const FactorDesc* __restrict__ descs, int num_factors, const double* __restrict__ poses, const double* __restrict__ poses_eval,
-  const int2* __restrict__ items, int num_items, int chunk,
+  const int2* __restrict__ items, int num_items, int chunk, int strided,
   unsigned long long* __restrict__ item_ctr, unsigned long long ctr_base,
   double* __restrict__ accum, int acc_slots, unsigned* __restrict__ done, double* __restrict__ out, float* __restrict__ slab, const PeerPush* __restrict__ peer) {
   __shared__ __align__(16) uint2 s_q[kWarps][kSubMax];
   __shared__ CtaCache cache_s;
   CtaCache* const cache = &cache_s;
   constexpr int U = kLookupUnroll;
+  constexpr int kGroupsPerRound = kSubMax / (32 * U);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   uint2* __restrict__ q = s_q[warp];
@@ -773,6 +781,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep5(
     }
     __syncthreads();  // the only block-level barrier of the kernel
   }
+  // descriptor reads keep their address space (LDS from the cache or LDG from the table)
   auto desc_of = [&](int f) -> FactorDesc { FactorDesc d; if (cached) d = cache->desc[f]; else d = descs[f]; return d; };
   auto publish = [&](int pf) -> int {  // lane 0, after a __syncwarp
     const unsigned t = ticket_release(&done[pf]);
@@ -804,24 +813,34 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep5(
     if (cached) P = cache->pose[f]; else P = pose_from_colmajor(poses + (size_t)f * 16);
     PoseF Pe = P;
     if (MODE == GB_MODE_ERROR) { if (cached) Pe = cache->pose_eval[f]; else Pe = pose_from_colmajor(poses_eval + (size_t)f * 16); }
-    const int item_end = min(it.y + chunk, D.n);
+
+    // the item's points: contiguous [it.y, it.y + chunk) or the rows it.y, it.y + J, ... (32 points each) of the cloud
+    const int limit = strided ? D.n : min(it.y + chunk, D.n);
+    const int row_stride = strided ? D.num_tiles * 32 : 32;
+    const int first = strided ? it.y * 32 : it.y;
+    int ngroups = 0;
+    if (first < limit) {
+      const int rows = (limit - first + row_stride - 1) / row_stride;  // strided: ceil((R - j) / J); contiguous: ceil(len / 32)
+      ngroups = (rows + U - 1) / U;
+    }
 
     float acc[32];
 #pragma unroll
     for (int k = 0; k < 32; k++) acc[k] = 0.f;
     bool published = (pend_f < 0);
 
-    for (int wb = it.y; wb < item_end; wb += kSubMax) {
-      const int we = min(wb + kSubMax, item_end);
+    for (int g0 = 0; g0 < ngroups; g0 += kGroupsPerRound) {
+      const int g1 = min(g0 + kGroupsPerRound, ngroups);
       int nq = 0;  // warp-uniform queue length
       // ---------------- phase A, software pipelined: group g's buckets and group g+1's points are in flight together ----
       float ax[U], ay[U], az[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const float4 a0 = __ldg(&D.p0[min(wb + u * 32 + lane, we - 1)]);
+        const int i = first + (g0 * U + u) * row_stride + lane;
+        const float4 a0 = __ldg(&D.p0[i < limit ? i : 0]);
         ax[u] = a0.x; ay[u] = a0.y; az[u] = a0.z;
       }
-      for (int i0 = wb; i0 < we; i0 += 32 * U) {
+      for (int g = g0; g < g1; g++) {
         int cx[U], cy[U], cz[U];
         uint32_t h[U];
         int4 b[U], b1[U];
@@ -836,10 +855,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep5(
           b[u] = __ldg(&D.buckets[h[u] & D.mask]);
           b1[u] = __ldg(&D.buckets[(h[u] + 1u) & D.mask]);
         }
-        if (i0 + 32 * U < we) {
+        if ((PIPE & 1) && g + 1 < g1) {
 #pragma unroll
           for (int u = 0; u < U; u++) {
-            const float4 a0 = __ldg(&D.p0[min(i0 + 32 * U + u * 32 + lane, we - 1)]);
+            const int i = first + ((g + 1) * U + u) * row_stride + lane;
+            const float4 a0 = __ldg(&D.p0[i < limit ? i : 0]);
             ax[u] = a0.x; ay[u] = a0.y; az[u] = a0.z;
           }
         }
@@ -850,31 +870,63 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep5(
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          const int i = i0 + u * 32 + lane;
+          const int i = first + (g * U + u) * row_stride + lane;
           int v = resolve_probe(D, b[u], b1[u], h[u], cx[u], cy[u], cz[u]);
-          if (i >= we) v = -1;
+          if (i >= limit) v = -1;
           const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
           if (v >= 0) q[nq + __popc(m & lt_mask)] = make_uint2((unsigned)i, (unsigned)v);
           nq += __popc(m);
         }
+        if (!(PIPE & 1) && g + 1 < g1) {  // not pipelined: the next group's points are loaded after this group is resolved
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const int i = first + ((g + 1) * U + u) * row_stride + lane;
+            const float4 a0 = __ldg(&D.p0[i < limit ? i : 0]);
+            ax[u] = a0.x; ay[u] = a0.y; az[u] = a0.z;
+          }
+        }
       }
       __syncwarp();
       // ---------------- phase B ----------------
+      if (!(PIPE & 2)) {
 #pragma unroll 2
-      for (int k = lane; k < nq; k += 32) {
-        const uint2 e = q[k];
-        const int i = (int)e.x;
-        const float4 a0 = __ldg(&D.p0[i]);
-        const float4 a1 = __ldg(&D.p1[i]);
-        const float a2 = __ldg(&D.p2[i]);
-        const float4 v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]);
-        const float4 v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]);
-        const float4 v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
-        accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
+        for (int k = lane; k < nq; k += 32) {
+          const uint2 e = q[k];
+          const float4 a0 = __ldg(&D.p0[e.x]);
+          const float4 a1 = __ldg(&D.p1[e.x]);
+          const float a2 = __ldg(&D.p2[e.x]);
+          const float4 v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]);
+          const float4 v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]);
+          const float4 v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
+          accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
+        }
+      } else {  // software pipelined: the lane's next hit is in flight while the current one is processed
+        int k = lane;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, v0 = a0, v1 = a0, v2 = a0;
+        float a2 = 0.f;
+        if (k < nq) {
+          const uint2 e = q[k];
+          a0 = __ldg(&D.p0[e.x]); a1 = __ldg(&D.p1[e.x]); a2 = __ldg(&D.p2[e.x]);
+          v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]); v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]); v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
+        }
+#pragma unroll 1
+        while (k < nq) {
+          const int kn = k + 32;
+          float4 na0 = a0, na1 = a1, nv0 = v0, nv1 = v1, nv2 = v2;
+          float na2 = a2;
+          if (kn < nq) {
+            const uint2 e = q[kn];
+            na0 = __ldg(&D.p0[e.x]); na1 = __ldg(&D.p1[e.x]); na2 = __ldg(&D.p2[e.x]);
+            nv0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]); nv1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]); nv2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
+          }
+          accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
+          a0 = na0; a1 = na1; a2 = na2; v0 = nv0; v1 = nv1; v2 = nv2;
+          k = kn;
+        }
       }
       __syncwarp();  // the queue is overwritten by the next round
     }
-    if (!published) {  // empty factor
+    if (!published) {  // empty item
       __syncwarp();
       if (lane == 0) pend_last = publish(pend_f);
     }
@@ -969,9 +1021,9 @@ static cudaError_t launch4(gb_sweep* s, const double* poses_eval, float* slab, c
   return cudaGetLastError();
 }
 
-template <int MODE, bool PEER>
+template <int MODE, bool PEER, int PIPE>
 static cudaError_t launch5(gb_sweep* s, const double* poses_eval, float* slab, const PeerPush* pp) {
-  k_vgicp_sweep5<MODE, PEER><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, (int)s->F, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
+  k_vgicp_sweep5<MODE, PEER, PIPE><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, (int)s->F, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->strided, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
   return cudaGetLastError();
 }
 
@@ -1013,8 +1065,12 @@ gb_status gb_launch_sweep(gb_sweep* s, int mode) {
     if (mode == GB_MODE_LINEARIZE) e = peer ? launch3<GB_MODE_LINEARIZE, true>(s, pe, slab, pp) : launch3<GB_MODE_LINEARIZE, false>(s, pe, slab, pp);
     else e = launch3<GB_MODE_ERROR, false>(s, pe, slab, pp);
   } else if (s->kernel_version == 5) {
-    if (mode == GB_MODE_LINEARIZE) e = peer ? launch5<GB_MODE_LINEARIZE, true>(s, pe, slab, pp) : launch5<GB_MODE_LINEARIZE, false>(s, pe, slab, pp);
-    else e = launch5<GB_MODE_ERROR, false>(s, pe, slab, pp);
+    if (mode == GB_MODE_ERROR) e = launch5<GB_MODE_ERROR, false, 0>(s, pe, slab, pp);
+    else if (peer) e = launch5<GB_MODE_LINEARIZE, true, 0>(s, pe, slab, pp);
+    else if (s->pipe == 1) e = launch5<GB_MODE_LINEARIZE, false, 1>(s, pe, slab, pp);
+    else if (s->pipe == 2) e = launch5<GB_MODE_LINEARIZE, false, 2>(s, pe, slab, pp);
+    else if (s->pipe == 3) e = launch5<GB_MODE_LINEARIZE, false, 3>(s, pe, slab, pp);
+    else e = launch5<GB_MODE_LINEARIZE, false, 0>(s, pe, slab, pp);
   } else if (s->stage_points == 64) {
     if (mode == GB_MODE_LINEARIZE) e = peer ? launch4<GB_MODE_LINEARIZE, 64, true, 3>(s, pe, slab, pp) : launch4<GB_MODE_LINEARIZE, 64, false, 3>(s, pe, slab, pp);
     else e = launch4<GB_MODE_ERROR, 64, false, 3>(s, pe, slab, pp);

@@ -21,15 +21,29 @@ from .gpu import Context, default_context
 
 @dataclasses.dataclass
 class CloudPreprocessorParams:
-    """Defaults of config/config_preprocess.json (read at cloud_preprocessor.cpp:28-71), except that the
-    downsampling defaults to the deterministic voxel grid BASELINE.json names."""
-    distance_near_thresh: float = 0.5
-    distance_far_thresh: float = 100.0
+    """glim::CloudPreprocessorParams.  Field defaults are the CODE defaults of cloud_preprocessor.cpp:28-61 (what the reference
+    uses when a key is missing); `from_shipped_config()` gives the values of config/config_preprocess.json:19-34 (random grid,
+    1.0 m, target 10 000, k = 10, near 0.5 m), which is what GLIM runs with out of the box."""
+    distance_near_thresh: float = 1.0        # :28
+    distance_far_thresh: float = 100.0       # :29
     global_shutter: bool = False
-    use_random_grid_downsampling: bool = False
-    downsample_resolution: float = 0.15
-    k_correspondences: int = 10
-    num_threads: int = 2
+    use_random_grid_downsampling: bool = False  # :30
+    downsample_resolution: float = 0.15      # :31
+    downsample_target: int = 0               # :32
+    downsample_rate: float = 0.3             # :33
+    enable_outlier_removal: bool = False     # :34  (True is rejected: the rule lives in the un-vendored gtsam_points)
+    enable_cropbox_filter: bool = False      # :38
+    crop_bbox_frame: str = "lidar"           # :39
+    crop_bbox_min: tuple = (0.0, 0.0, 0.0)
+    crop_bbox_max: tuple = (0.0, 0.0, 0.0)
+    T_imu_lidar: tuple = tuple(np.eye(4).reshape(-1))
+    k_correspondences: int = 8               # :59
+    num_threads: int = 2                     # :61
+
+    @staticmethod
+    def from_shipped_config() -> "CloudPreprocessorParams":
+        return CloudPreprocessorParams(distance_near_thresh=0.5, distance_far_thresh=100.0, use_random_grid_downsampling=True, downsample_resolution=1.0, downsample_target=10000,
+                                       downsample_rate=0.1, crop_bbox_min=(-1.0, -1.0, -1.0), crop_bbox_max=(1.0, 1.0, 1.0), k_correspondences=10)
 
 
 @dataclasses.dataclass
@@ -99,32 +113,97 @@ class CloudCovarianceEstimation:
 
 
 class CloudPreprocessor:
-    """glim::CloudPreprocessor (voxel-grid path)."""
+    """glim::CloudPreprocessor::preprocess (cloud_preprocessor.cpp:77-188) -> PreprocessedFrame.  One gb_preprocess call: the
+    whole pipeline runs on the device; only the PreprocessedFrame fields come back."""
 
-    def __init__(self, params: CloudPreprocessorParams | None = None, ctx: Context | None = None):
+    def __init__(self, params: CloudPreprocessorParams | None = None, ctx: Context | None = None, seed: int = 0):
         self.params = params or CloudPreprocessorParams()
         self.ctx = ctx
+        self.seed = seed
 
     def preprocess(self, stamp: float, times, points, intensities=None) -> PreprocessedFrame:
-        p = self.params
+        if self.params.enable_outlier_removal:
+            raise NotImplementedError("statistical outlier removal (cloud_preprocessor.cpp:165-167) is not implemented: its rule lives in the un-vendored gtsam_points")
+        from .capi import Preprocessed
+
         ctx = self.ctx or default_context()
-        if p.use_random_grid_downsampling:
-            raise NotImplementedError("randomgrid_sampling draws from std::mt19937 and is not reproducible across implementations (SURVEY C.2); use the voxel grid")
-        # downsampling (:104-109)
-        pts, tms, ints = voxelgrid_sampling(points, p.downsample_resolution, times, intensities, ctx)
-        # distance filter (:116-128)
-        sq = np.einsum("ij,ij->i", pts[:, :3], pts[:, :3])
-        keep = (sq > p.distance_near_thresh**2) & (sq < p.distance_far_thresh**2) & np.isfinite(pts).all(axis=1)
-        idx = np.nonzero(keep)[0]
-        # sort by time (:135-136; std::sort is not stable in the reference, ties are unspecified -- we use a stable sort)
-        idx = idx[np.argsort(tms[idx], kind="stable")]
-        pts, tms = pts[idx], tms[idx]
-        ints = ints[idx] if ints is not None else None
-        if p.global_shutter:  # :138-140
-            tms = np.zeros_like(tms)
-        scan_end = stamp + (tms[-1] if len(tms) else 0.0)  # :174
-        nb = find_neighbors(pts, p.k_correspondences, ctx)  # :182-183
-        return PreprocessedFrame(stamp, scan_end, tms, ints, np.ascontiguousarray(pts), p.k_correspondences, nb)
+        g = FramePreprocessorGPU(self.params, ctx, self.seed)
+        cp = g.c_params()
+        cp.estimate_covariances = 0
+        points = f64(points)
+        n = points.shape[0]
+        t = f64(times) if times is not None else None
+        it = f64(intensities) if intensities is not None else None
+        k = cp.k_correspondences
+        out = Preprocessed()
+        o_t, o_p, o_i, o_n = np.empty(n), np.empty((n, 4)), (np.empty(n) if it is not None else None), np.empty((n, k), np.int32)
+        out.times, out.xyzw, out.intensities, out.neighbors = o_t.ctypes.data, o_p.ctypes.data, (o_i.ctypes.data if o_i is not None else None), o_n.ctypes.data
+        check(lib().gb_preprocess(ctx.h, n, ptr(points), ptr(t), ptr(it), C.byref(cp), C.byref(out)))
+        m = out.num_points
+        return PreprocessedFrame(stamp, stamp + out.last_time, o_t[:m].copy(), o_i[:m].copy() if o_i is not None else None, np.ascontiguousarray(o_p[:m]), k, o_n[:m].reshape(-1).copy())
+
+
+class FramePreprocessorGPU:
+    """gb_preprocess: CloudPreprocessor::preprocess_impl + CloudCovarianceEstimation::estimate + PointCloudGPU::clone in one
+    device-resident call (include/glim_b200.h).  `params` is the CloudPreprocessorParams of this module; `host_outputs`
+    selects whether the PreprocessedFrame fields / fp64 covariances are copied back (the device cloud is always produced)."""
+
+    def __init__(self, params: "CloudPreprocessorParams | None" = None, ctx: Context | None = None, seed: int = 0, knn_cell_size: float = 0.0):
+        self.params = params or CloudPreprocessorParams()
+        self.ctx = ctx
+        self.seed = seed
+        self.knn_cell_size = knn_cell_size
+
+    def c_params(self):
+        from .capi import PreprocessParams
+
+        p = self.params
+        cp = PreprocessParams()
+        check(lib().gb_preprocess_default_params(C.byref(cp)))
+        cp.distance_near_thresh, cp.distance_far_thresh = p.distance_near_thresh, p.distance_far_thresh
+        cp.use_random_grid_downsampling = int(p.use_random_grid_downsampling)
+        cp.downsample_resolution, cp.downsample_target, cp.downsample_rate = p.downsample_resolution, p.downsample_target, p.downsample_rate
+        cp.seed = self.seed
+        cp.global_shutter = int(p.global_shutter)
+        cp.crop_bbox_frame = {"": 0, "lidar": 1, "imu": 2}[p.crop_bbox_frame] if p.enable_cropbox_filter else 0
+        for a in range(3):
+            cp.crop_bbox_min[a], cp.crop_bbox_max[a] = p.crop_bbox_min[a], p.crop_bbox_max[a]
+        T = np.asarray(p.T_imu_lidar, dtype=np.float64).reshape(4, 4)
+        for c in range(4):
+            for r in range(4):
+                cp.T_imu_lidar[c * 4 + r] = T[r, c]
+        cp.enable_outlier_removal = int(p.enable_outlier_removal)
+        cp.k_correspondences = p.k_correspondences
+        cp.estimate_covariances = 1
+        cp.knn_cell_size = self.knn_cell_size
+        return cp
+
+    def preprocess(self, stamp: float, times, points, intensities=None, host_outputs: bool = True):
+        """-> (PreprocessedFrame or None, normals (M,4), covs (M,4,4), gpu.PointCloudGPU)"""
+        from . import gpu
+        from .capi import Preprocessed
+
+        ctx = self.ctx or default_context()
+        points = f64(points)
+        n = points.shape[0]
+        t = f64(times) if times is not None else None
+        it = f64(intensities) if intensities is not None else None
+        cp = self.c_params()
+        k = cp.k_correspondences
+        out = Preprocessed()
+        bufs = {}
+        if host_outputs:
+            bufs = {"times": np.empty(n), "xyzw": np.empty((n, 4)), "intensities": np.empty(n) if it is not None else None, "neighbors": np.empty((n, k), np.int32), "normals4": np.empty((n, 4)), "cov4x4": np.empty((n, 16))}
+            for name, b in bufs.items():
+                setattr(out, name, b.ctypes.data if b is not None else None)
+        check(lib().gb_preprocess(ctx.h, n, ptr(points), ptr(t), ptr(it), C.byref(cp), C.byref(out)))
+        m = out.num_points
+        cloud = gpu.PointCloudGPU(ctx, C.c_void_p(out.cloud), m) if out.cloud else None
+        if not host_outputs:
+            return None, None, None, cloud
+        fr = PreprocessedFrame(stamp, stamp + out.last_time, bufs["times"][:m].copy(), bufs["intensities"][:m].copy() if it is not None else None, bufs["xyzw"][:m].copy(), k, bufs["neighbors"][:m].reshape(-1).copy())
+        covs = bufs["cov4x4"][:m].reshape(m, 4, 4).transpose(0, 2, 1).copy()
+        return fr, bufs["normals4"][:m].copy(), covs, cloud
 
 
 def _poses16(poses):

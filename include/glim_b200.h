@@ -197,6 +197,49 @@ GB_API gb_status gb_find_neighbors(gb_ctx* ctx, size_t n, const double* xyzw, in
  *      points / times / intensities, ascending packed-key order.  out arrays sized n; *num_out = count ---- */
 GB_API gb_status gb_voxelgrid_sampling(gb_ctx* ctx, size_t n, const double* xyzw, const double* times, const double* intensities, double resolution, double* out_xyzw, double* out_times, double* out_intensities, size_t* num_out);
 
+/* ---- The whole per-frame preprocess in one call, kept on the device (SURVEY 8(b) gb_preprocess):
+ *      glim::CloudPreprocessor::preprocess_impl (src/glim/preprocess/cloud_preprocessor.cpp:92-188: voxel-grid :108 or
+ *      random-grid :104-106 downsampling, finite + range gate :116-128, time order :135-136, global shutter :138-140,
+ *      crop box :143-162, k-NN :182-183) fused with glim::CloudCovarianceEstimation::estimate
+ *      (src/glim/common/cloud_covariance_estimation.cpp:43-122, called at src/glim/odometry/odometry_estimation_imu.cpp:322-328)
+ *      and PointCloudGPU::clone (odometry_estimation_gpu.cpp:96): one H2D of the raw scan, no host round trip between the
+ *      stages, the fp32 planes of the resulting gb_cloud written by the covariance kernel.  Host products (the
+ *      PreprocessedFrame fields, fp64 covariances / normals) are copied back only for the pointers that are not NULL.
+ *      Not implemented: statistical outlier removal (:165-167; its rule lives in the un-vendored gtsam_points) -> the call
+ *      fails with GB_ERR_INVALID_ARGUMENT when enable_outlier_removal is set.
+ *      Random grid: which points of a voxel survive is a draw from std::mt19937 in the reference (not reproducible); here it
+ *      is the ceil(rate N / V) points with the smallest hash(seed, index) -- same count per voxel, a fixed pseudo-random pick. ---- */
+typedef struct gb_preprocess_params {
+  double distance_near_thresh, distance_far_thresh; /* config_preprocess.json:20-21 */
+  int use_random_grid_downsampling;                 /* config_preprocess.json:22 */
+  double downsample_resolution;                     /* <= 0: no downsampling */
+  int downsample_target;                            /* > 0: rate = target / N (cloud_preprocessor.cpp:105) */
+  double downsample_rate;
+  uint64_t seed;                                    /* random grid */
+  int global_shutter;
+  int crop_bbox_frame;                              /* 0 = off, 1 = "lidar", 2 = "imu" */
+  double crop_bbox_min[3], crop_bbox_max[3];
+  double T_imu_lidar[16];                           /* column-major; used by crop_bbox_frame == 2 */
+  int enable_outlier_removal;                       /* must be 0 */
+  int k_correspondences;                            /* k of the k-NN (10) */
+  int estimate_covariances;                         /* fuse CloudCovarianceEstimation + the device cloud */
+  int k_neighbors_cov;                              /* neighbours used by the covariance (<= k_correspondences; 0 = all) */
+  double knn_cell_size;                             /* finest cell of the k-NN grid pyramid, metres (0 = 0.25) */
+} gb_preprocess_params;
+typedef struct gb_preprocessed {
+  size_t num_points;     /* out */
+  double last_time;      /* out: times.back() (scan_end_time = stamp + last_time, cloud_preprocessor.cpp:174) */
+  double* times;         /* caller-allocated for n_raw entries, or NULL */
+  double* xyzw;          /* n_raw x 4 */
+  double* intensities;   /* n_raw */
+  int32_t* neighbors;    /* n_raw x k */
+  double* normals4;      /* n_raw x 4  (estimate_covariances) */
+  double* cov4x4;        /* n_raw x 16 (estimate_covariances) */
+  gb_cloud* cloud;       /* out: the frame as a device cloud (points + covariances + normals), or NULL; destroy with gb_cloud_destroy */
+} gb_preprocessed;
+GB_API gb_status gb_preprocess_default_params(gb_preprocess_params* params); /* config/config_preprocess.json + CloudPreprocessorParams defaults */
+GB_API gb_status gb_preprocess(gb_ctx* ctx, size_t n_raw, const double* xyzw, const double* times, const double* intensities, const gb_preprocess_params* params, gb_preprocessed* out);
+
 /* ---- glim::CloudDeskewing::deskew (src/glim/common/cloud_deskewing.cpp:11-55 constant velocity, :57-133 predicted IMU poses;
  *      called at src/glim/odometry/odometry_estimation_imu.cpp:313).  n_imu > 0: imu_times / imu_poses (n_imu x 16, T_world_imu)
  *      and `stamp` select the IMU-pose overload; n_imu == 0: linear_vel / angular_vel (either may be NULL = zero) select the

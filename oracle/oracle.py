@@ -63,6 +63,8 @@ def lib():
         L.go_knn_bruteforce.argtypes = [i32, vp, i32, i32, vp, vp]
         L.go_voxelgrid_sampling.restype = i32
         L.go_voxelgrid_sampling.argtypes = [i32, vp, vp, vp, f64, vp, vp, vp]
+        L.go_randomgrid_sampling.restype = i32
+        L.go_randomgrid_sampling.argtypes = [i32, vp, f64, f64, C.c_uint64, vp]
         L.go_deskew_const_vel.restype = i32
         L.go_deskew_const_vel.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
         L.go_deskew_imu.restype = i32
@@ -274,6 +276,14 @@ def voxelgrid_sampling(pts4, resolution, times=None, intensities=None):
     oi = np.empty((n,)) if it is not None else None
     m = lib().go_voxelgrid_sampling(n, _p(pts4), _p(t), _p(it), float(resolution), _p(op), _p(ot), _p(oi))
     return op[:m].copy(), (ot[:m].copy() if ot is not None else None), (oi[:m].copy() if oi is not None else None)
+
+
+def randomgrid_sampling(pts4, resolution, rate, seed=0):
+    """-> bool mask of the survivors (original order is kept), see go_randomgrid_sampling."""
+    pts4 = _f64(pts4)
+    keep = np.zeros(pts4.shape[0], np.int32)
+    lib().go_randomgrid_sampling(pts4.shape[0], _p(pts4), float(resolution), float(rate), int(seed), _p(keep))
+    return keep.astype(bool)
 
 
 def deskew_const_vel(T_imu_lidar, linear_vel, angular_vel, times, pts4, T_post=None):

@@ -14,9 +14,14 @@ import bench  # noqa: E402
 
 CONFIGS = [
     ("v3", {"GB_KERNEL": "3"}),
-    ("v5 ipw6", {"GB_KERNEL": "5", "GB_ITEMS_PER_WARP": "6"}),
-    ("v5 ipw2", {"GB_KERNEL": "5", "GB_ITEMS_PER_WARP": "2"}),
-    ("v5 ipw1", {"GB_KERNEL": "5", "GB_ITEMS_PER_WARP": "1"}),
+    ("v5", {"GB_KERNEL": "5"}),
+    ("v5 pipe1", {"GB_KERNEL": "5", "GB_PIPE": "1"}),
+    ("v5 pipe2", {"GB_KERNEL": "5", "GB_PIPE": "2"}),
+    ("v5 pipe3", {"GB_KERNEL": "5", "GB_PIPE": "3"}),
+    ("v5 nostride", {"GB_KERNEL": "5", "GB_STRIDED": "0"}),
+    ("v5 minrows1", {"GB_KERNEL": "5", "GB_MIN_ROWS": "1"}),
+    ("v5 minrows8", {"GB_KERNEL": "5", "GB_MIN_ROWS": "8"}),
+    ("v5 ipw2", {"GB_KERNEL": "5", "GB_STRIDED": "0", "GB_ITEMS_PER_WARP": "2"}),
     ("v4 T128 ipw4", {"GB_KERNEL": "4", "GB_STAGE": "128", "GB_ITEMS_PER_WARP": "4"}),
     ("v4 T128 ipw1", {"GB_KERNEL": "4", "GB_STAGE": "128", "GB_ITEMS_PER_WARP": "1"}),
     ("v4 T128 ipw2", {"GB_KERNEL": "4", "GB_STAGE": "128", "GB_ITEMS_PER_WARP": "2"}),
@@ -24,7 +29,7 @@ CONFIGS = [
     ("v4 T64 ipw4", {"GB_KERNEL": "4", "GB_STAGE": "64", "GB_ITEMS_PER_WARP": "4"}),
     ("v4 T64 ipw2", {"GB_KERNEL": "4", "GB_STAGE": "64", "GB_ITEMS_PER_WARP": "2"}),
 ]
-KEYS = ["GB_KERNEL", "GB_STAGE", "GB_ITEMS_PER_WARP", "GB_TILE"]
+KEYS = ["GB_KERNEL", "GB_STAGE", "GB_ITEMS_PER_WARP", "GB_TILE", "GB_STRIDED", "GB_MIN_ROWS", "GB_PIPE"]
 
 
 def main():
@@ -58,6 +63,9 @@ def main():
                 for s in sweeps:
                     s.launch()
 
+            step()
+            for sw in sweeps:
+                sw.fetch()
             for _ in range(5):
                 step()
             steps = 30

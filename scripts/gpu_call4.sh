@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
+AB_CONFIGS="v3,v5,v5 nostride,v5 minrows1,v5 minrows8,v5 ipw2" timeout 600 python scripts/ab_sweep.py > gpurun_out/ab_r02c.txt 2> gpurun_out/ab_r02c.err; echo "ab rc=$?"; grep -v "^#" gpurun_out/ab_r02c.txt | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print(d['workload'][:12].ljust(12), d['config'].ljust(14), str(d['M_pf_s']).rjust(8), str(d['us_per_launch']).rjust(9), d['frac'], d['items_grid'], d['same_as_first'])"
+tail -3 gpurun_out/ab_r02c.err

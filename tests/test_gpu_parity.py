@@ -308,7 +308,7 @@ def test_preprocess_pipeline(ctx, pair):
     from glim_b200 import preprocess
 
     P, T = pair["points"][0], pair["times"][0]
-    fr = preprocess.CloudPreprocessor(preprocess.CloudPreprocessorParams(downsample_resolution=0.3, distance_near_thresh=2.0, distance_far_thresh=30.0), ctx=ctx).preprocess(100.0, T, P)
+    fr = preprocess.CloudPreprocessor(preprocess.CloudPreprocessorParams(downsample_resolution=0.3, distance_near_thresh=2.0, distance_far_thresh=30.0, k_correspondences=10), ctx=ctx).preprocess(100.0, T, P)
     d = np.linalg.norm(fr.points[:, :3], axis=1)
     assert (d > 2.0).all() and (d < 30.0).all() and (np.diff(fr.times) >= 0).all()
     assert fr.scan_end_time == 100.0 + fr.times[-1] and fr.neighbors.shape == (fr.size() * 10,)
@@ -408,8 +408,8 @@ def test_kernel_generations_agree(ctx, dev, monkeypatch):
     maps0 = [gpu.GaussianVoxelMapGPU(r, ctx=ctx).insert(dev["cloud"][0]) for r in (0.25, 0.5)]
     T = dev["T_gt"]
     outs = {}
-    for name, env in (("v4_128", {"GB_KERNEL": "4", "GB_STAGE": "128"}), ("v4_64", {"GB_KERNEL": "4", "GB_STAGE": "64"}), ("v3", {"GB_KERNEL": "3"}), ("v5", {"GB_KERNEL": "5"}), ("v5_big_items", {"GB_KERNEL": "5", "GB_TILE": "2048"}), ("v4_big_items", {"GB_KERNEL": "4", "GB_TILE": "2048"})):
-        for k in ("GB_KERNEL", "GB_STAGE", "GB_TILE"):
+    for name, env in (("v4_128", {"GB_KERNEL": "4", "GB_STAGE": "128"}), ("v4_64", {"GB_KERNEL": "4", "GB_STAGE": "64"}), ("v3", {"GB_KERNEL": "3"}), ("v5", {"GB_KERNEL": "5"}), ("v5_contiguous", {"GB_KERNEL": "5", "GB_STRIDED": "0"}), ("v5_big_items", {"GB_KERNEL": "5", "GB_STRIDED": "0", "GB_TILE": "2048"}), ("v4_big_items", {"GB_KERNEL": "4", "GB_TILE": "2048"})):
+        for k in ("GB_KERNEL", "GB_STAGE", "GB_TILE", "GB_STRIDED"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -418,7 +418,7 @@ def test_kernel_generations_agree(ctx, dev, monkeypatch):
         outs[name] = fs.linearize_deltas(np.stack([T, T]))
         e = fs.error_deltas(np.stack([T, T]), np.stack([T, T]))
         assert np.allclose(e, outs[name]["error"], rtol=1e-5)
-    for name in ("v4_64", "v3", "v5", "v5_big_items", "v4_big_items"):
+    for name in ("v4_64", "v3", "v5", "v5_contiguous", "v5_big_items", "v4_big_items"):
         for i in range(2):
             assert outs[name][i]["num_inliers"] == outs["v4_128"][i]["num_inliers"]
             for k in ("H_tt", "H_ss", "H_ts"):
@@ -449,18 +449,30 @@ def _oracle_check_factors(ctx, w, fset, picks, tol=REL_TOL):
     return sw, rec, worst
 
 
-def test_global_mapping_factors_match_oracle(ctx):
-    """M4 data distribution at full submap size (50 k points, 0.5 / 1.0 m voxels, ~35 % inliers) on a short loop: the batched
-    sweep runs through the dynamic item queue (items > warps) and replicated accumulators; picked factors vs the oracle."""
+@pytest.mark.parametrize("strided", ["1", "0"])
+def test_global_mapping_factors_match_oracle(ctx, monkeypatch, strided):
+    """M4 data distribution at full submap size (50 k points, 0.5 / 1.0 m voxels, ~35 % inliers) on a short loop.  strided=0:
+    the batched sweep runs through the dynamic item queue (items > warps) and replicated accumulators; strided=1 (what a
+    sweep of this size gets by default): one wave of strided items, re-sized after the first fetch.  Picked factors vs the oracle."""
     from glim_b200 import workloads
 
+    monkeypatch.setenv("GB_STRIDED", strided)
     w = workloads.global_mapping(ctx, n_submaps=12, laps=1, side=60.0, use_gpu=True)
     fset = w.sets[0]
     assert len(fset.factors) >= 10 and min(len(c[0]) for c in w.host_clouds) == 50000
     rng = np.random.default_rng(5)
     picks = sorted(rng.choice(len(fset.factors), 6, replace=False).tolist())
     sw, rec, worst = _oracle_check_factors(ctx, w, fset, picks)
-    assert sw.num_tiles > sw.grid * 8  # the queue path
+    if strided == "0":
+        assert sw.num_tiles > sw.grid * 8  # the queue path
+    else:
+        assert sw.num_tiles <= sw.grid * 8  # one wave
+        # the fetch above re-sized the item table from the measured inlier fractions: same results from the new table
+        sw.launch()
+        rec2 = sw.fetch()
+        assert np.array_equal(rec2["num_inliers"], rec["num_inliers"])
+        for k in ("H_tt", "H_ss"):
+            assert util.rel_err(np.asarray(rec2[k]), np.asarray(rec[k])) < 1e-5
     inl = rec["num_inliers"] / 50000.0
     assert 0.05 < np.median(inl) < 0.9
 
@@ -475,3 +487,80 @@ def test_livox_dense_factor_matches_oracle(ctx):
     picks = [k for k, f in enumerate(fset.factors) if f.target == 0]
     assert len(picks) == 2
     _oracle_check_factors(ctx, w, fset, picks)
+
+
+# ---------------------------------------------------------------------------------------------- gb_preprocess (device-resident frame pipeline)
+def _cpu_frame(P, T, res, near, far, k, mask=None, crop=None):
+    """oracle composition of CloudPreprocessor::preprocess_impl + CloudCovarianceEstimation::estimate"""
+    if mask is None:
+        pts, tms, _ = oracle.voxelgrid_sampling(P, res, times=T)
+    else:
+        pts, tms = P[mask], T[mask]
+    sq = (pts[:, :3] ** 2).sum(1)
+    keep = (sq > near * near) & (sq < far * far) & np.isfinite(pts).all(axis=1)
+    if crop is not None:
+        lo, hi = crop
+        keep &= ~((pts[:, :3] >= lo).all(1) & (pts[:, :3] <= hi).all(1))
+    idx = np.nonzero(keep)[0]
+    idx = idx[np.argsort(tms[idx], kind="stable")]
+    pts, tms = np.ascontiguousarray(pts[idx]), tms[idx]
+    nb, _ = oracle.knn_bruteforce(pts, k)
+    normals, covs = oracle.covariance_estimate(pts, nb)
+    return pts, tms, nb, normals, covs
+
+
+@pytest.mark.parametrize("mode", ["voxelgrid", "randomgrid", "cropbox"])
+def test_gb_preprocess_matches_oracle_pipeline(ctx, mode):
+    """One device-resident call = the reference's whole per-frame preprocess + covariance estimation + PointCloudGPU::clone:
+    frame points / times bit-exact, neighbour indices exact, covariances 1e-9, and the device cloud equals the fp32 cast of
+    the host products."""
+    from glim_b200 import preprocess
+
+    sc = synth.make_hall_scene()
+    P, T = synth.scan(sc, "hdl32", synth.arc_trajectory(8)[2], synth.rng_for(41), n_rays=32 * 700)
+    P = P.copy()
+    P[17, 1] = np.nan  # a non-finite raw point is dropped by the gate (cloud_preprocessor.cpp:123)
+    k = 10
+    if mode == "randomgrid":
+        par = preprocess.CloudPreprocessorParams(distance_near_thresh=1.0, distance_far_thresh=60.0, use_random_grid_downsampling=True, downsample_resolution=1.0, downsample_target=6000, k_correspondences=k)
+        mask = oracle.randomgrid_sampling(P, 1.0, 6000 / len(P), seed=5)
+        assert 5000 < mask.sum() <= int(len(P) * (6000 / len(P)) * 1.2)
+        ref = _cpu_frame(P, T, None, 1.0, 60.0, k, mask=mask)
+    elif mode == "cropbox":
+        par = preprocess.CloudPreprocessorParams(distance_near_thresh=1.0, distance_far_thresh=60.0, downsample_resolution=0.2, k_correspondences=k, enable_cropbox_filter=True, crop_bbox_min=(-3.0, -2.0, -5.0), crop_bbox_max=(4.0, 2.5, 5.0))
+        ref = _cpu_frame(P, T, 0.2, 1.0, 60.0, k, crop=(np.array([-3.0, -2.0, -5.0]), np.array([4.0, 2.5, 5.0])))
+    else:
+        par = preprocess.CloudPreprocessorParams(distance_near_thresh=1.0, distance_far_thresh=60.0, downsample_resolution=0.2, k_correspondences=k)
+        ref = _cpu_frame(P, T, 0.2, 1.0, 60.0, k)
+    fr, normals, covs, cloud = preprocess.FramePreprocessorGPU(par, ctx, seed=5).preprocess(10.0, T, P)
+    pts, tms, nb, n_ref, c_ref = ref
+    assert fr.size() == len(pts) > 3000
+    assert np.array_equal(fr.points, pts) and np.array_equal(fr.times, tms) and fr.scan_end_time == 10.0 + tms[-1]
+    assert np.array_equal(fr.neighbors.reshape(-1, k), nb)
+    assert np.allclose(covs, c_ref, atol=1e-9)
+    assert np.allclose(np.abs(np.einsum("ni,ni->n", normals[:, :3], n_ref[:, :3])), 1.0, atol=1e-9)
+    gx, gc = cloud.download()
+    xyz, cov6 = oracle.pack_cloud(fr.points, util.cov_colmajor16(covs))
+    assert np.array_equal(gx, xyz) and np.array_equal(gc, cov6)  # the planes were written from the same fp64 values
+    # and the frame is usable as a VGICP source right away
+    m = gpu.GaussianVoxelMapGPU(0.5, ctx=ctx).insert(cloud)
+    got = gpu.IntegratedVGICPFactorGPU(np.eye(4), 1, m, cloud, ctx=ctx).linearize({1: np.eye(4)})
+    assert got["num_inliers"] == fr.size()
+    # the PreprocessedFrame-only entry (CloudPreprocessor mirror) agrees
+    fr2 = preprocess.CloudPreprocessor(par, ctx=ctx, seed=5).preprocess(10.0, T, P)
+    assert np.array_equal(fr2.points, fr.points) and np.array_equal(fr2.neighbors, fr.neighbors)
+
+
+def test_pyramid_knn_is_exact_on_hard_clouds(ctx, monkeypatch):
+    """The grid-pyramid k-NN on duplicated points, far outliers (coarsest-level / full-scan fallback), tiny clouds."""
+    from glim_b200 import preprocess
+
+    monkeypatch.setenv("GB_KNN", "pyramid")
+    P = util.scan_pair(n_rays=32 * 100)["points"][0]
+    rng = synth.rng_for(31)
+    dup = np.concatenate([P[:500], P[:500], P[100:200] + [1e-9, 0, 0, 0], [[500.0, -300.0, 20.0, 1.0], [-800.0, 10.0, 5.0, 1.0]], rng.normal(0, 0.01, (64, 4)) * [1, 1, 1, 0] + [3, 3, 3, 1]])
+    for cloud in (P, dup, P[:7]):
+        for k in (10, 5):
+            nb = preprocess.find_neighbors(cloud, k, ctx=ctx).reshape(len(cloud), k)
+            ref, _ = oracle.knn_bruteforce(cloud, k)
+            assert np.array_equal(nb, ref)
