@@ -435,7 +435,7 @@ def roofline_of(name, my_bytes, miss_bytes, k_launches, kernel_ms_per_launch, wo
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = my_bytes / max(1, k_launches) / (kernel_ms_per_launch * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(name, world, scale)
-    r = {"bound": "hbm", "kernel": "k_vgicp_sweep5<LINEARIZE>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    r = {"bound": "hbm", "kernel": "k_vgicp_sweep3 / k_vgicp_sweep5 <LINEARIZE>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
          "algorithmic_bytes_per_launch": my_bytes / max(1, k_launches), "launch_ms": kernel_ms_per_launch,
          "traffic": traffic, "traffic_source": traffic_src,
@@ -758,7 +758,7 @@ def main():
             "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.workload, w, {"parallelism": par,
                                                        "tiles_grid_first_sweep": [int(sweeps[0].num_tiles), int(sweeps[0].grid)], "partition": ("contiguous, cost = n_source + 1.25 * measured inliers (calibration sweep)" if calibrated else "contiguous, cost = n_source * (1 + 1.25 * gate overlap)") if sharded else None, "build_seconds": round(build_s, 1), "scale": args.scale,
-                                                       "kernel": os.environ.get("GB_KERNEL", "5")}),
+                                                       "kernel": os.environ.get("GB_KERNEL", "auto: k_vgicp_sweep5 + strided items for small sweeps, k_vgicp_sweep3 for large ones")}),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ems / e_steps,
                     "result": "pair slab (levels pre-summed on the device)" if sharded else "gb_linearized6 records"},
             "gpu_launches": int(gpu_launches),

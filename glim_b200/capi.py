@@ -24,7 +24,7 @@ SYMBOLS = [
     "gb_sweep_results_device", "gb_sweep_stats",
     "gb_peer_slab_create", "gb_peer_slab_export", "gb_peer_slab_connect", "gb_peer_slab_destroy", "gb_sweep_attach_peer_slab",
     "gb_peer_slab_signal_wait", "gb_peer_slab_device_ptr", "gb_peer_slab_fetch", "gb_peer_slab_fetch_async",
-    "gb_overlap", "gb_covariances", "gb_find_neighbors", "gb_voxelgrid_sampling", "gb_preprocess_default_params", "gb_preprocess",
+    "gb_overlap", "gb_covariances", "gb_find_neighbors", "gb_voxelgrid_sampling", "gb_preprocess_default_params", "gb_preprocess", "gb_merge_frames",
     "gb_deskew_pose_table", "gb_deskew",
 ]
 
@@ -83,6 +83,7 @@ def lib():
     L.gb_cloud_device_ptrs.argtypes = [vp, vp, vp, vp, vp]
     L.gb_preprocess_default_params.argtypes = [vp]
     L.gb_preprocess.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.gb_merge_frames.argtypes = [vp, sz, vp, vp, f64, i32, u64, vp, vp, vp, vp]
     L.gb_hessian_blocks.argtypes = [vp, f64, vp, vp, vp, vp, vp, vp]
     L.gb_slab_row_hessian_blocks.argtypes = [vp, f64, vp, vp, vp, vp, vp, vp, vp]
     L.gb_voxelmap_build.argtypes = [vp, vp, f32, i32, i32, f64, vp]

@@ -502,14 +502,18 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   s->pool_d = nullptr; s->pool_d_cap = 0; s->pool_h = nullptr; s->pool_h_cap = 0;
 
   // kernel generation and work-item policy
-  { const int kv = env_int("GB_KERNEL", 5); s->kernel_version = (kv == 3 || kv == 4) ? kv : 5; }
+  // Kernel policy (measured on B200, profiles/r02_ab_kernels.txt): small sweeps -- about one item per warp: an odometry
+  // frame, a single pair -- run k_vgicp_sweep5 with one wave of equally expensive STRIDED items (-25 % on the odometry
+  // workload); large sweeps run k_vgicp_sweep3 with contiguous 2048-point items drawn from the queue (its simpler hot loops
+  // are 5-9 % faster there).  GB_KERNEL = 3 / 4 / 5 forces one kernel (4 = the bulk-async staged experiment).
+  const int kv = env_int("GB_KERNEL", 0);
   s->stage_points = env_int("GB_STAGE", 128) == 64 ? 64 : 128;
-  const int ctas_per_sm = (s->kernel_version == 4 && s->stage_points == 64) ? 3 : 2;
+  const int ctas_per_sm = (kv == 4 && s->stage_points == 64) ? 3 : 2;
   s->capacity = ctx->num_sms * ctas_per_sm;
   const uint64_t warps = (uint64_t)s->capacity * 8;
-  // one wave of equally expensive STRIDED items when the sweep is small (an odometry frame, a single pair); contiguous items
-  // drawn from a queue otherwise
-  s->strided = (s->kernel_version == 5 && F > 0 && env_int("GB_STRIDED", 1) && total_pts <= warps * 2048) ? 1 : 0;
+  const bool small = F > 0 && total_pts <= warps * 2048;
+  s->kernel_version = (kv == 3 || kv == 4 || kv == 5) ? kv : (small ? 5 : 3);
+  s->strided = (s->kernel_version == 5 && small && env_int("GB_STRIDED", 1)) ? 1 : 0;
   s->calibrated = false;
   s->pipe = env_int("GB_PIPE", 0) & 3;
   s->h_descs = nullptr; s->h_tiles = nullptr; s->tiles_cap = 0;
@@ -991,6 +995,38 @@ extern "C" gb_status gb_find_neighbors(gb_ctx* ctx, size_t n, const double* xyzw
   const bool pyramid = mode ? (strcmp(mode, "pyramid") == 0) : (n >= 4096);
   if (pyramid) return gb_find_neighbors_pyramid_impl(ctx, n, xyzw, k, neighbors);
   return gb_find_neighbors_impl(ctx, n, xyzw, k, neighbors);
+}
+
+extern "C" gb_status gb_merge_frames(gb_ctx* ctx, size_t K, const gb_cloud* const* frames, const double* poses, double resolution, int target, uint64_t seed, double* out_xyzw, double* out_cov4x4, size_t* num_out, gb_cloud** out_cloud) {
+  GB_REQUIRE(ctx && num_out, "null argument");
+  *num_out = 0;
+  if (out_cloud) *out_cloud = nullptr;
+  if (K == 0) return GB_OK;
+  GB_REQUIRE(frames && poses, "null frames / poses");
+  GB_REQUIRE(resolution > 0.0, "downsample_resolution must be positive");
+  size_t total = 0;
+  for (size_t k = 0; k < K; k++) {
+    GB_REQUIRE(frames[k] && frames[k]->device == ctx->device, "null frame / frame on another device");
+    total += frames[k]->n;
+  }
+  GB_REQUIRE(total < (size_t)1 << 30 && K < 65536, "too many points / frames");
+  GB_LOCK(ctx);
+  GB_CUDA(cudaSetDevice(ctx->device));
+  gb_cloud* c = nullptr;
+  if (out_cloud) {
+    c = new (std::nothrow) gb_cloud();
+    if (!c) return GB_ERR_INTERNAL;
+    c->device = ctx->device; c->n = 0; c->base = nullptr; c->bytes = 0;
+    c->p0 = nullptr; c->p1 = nullptr; c->p2 = nullptr; c->normals = nullptr; c->perm = nullptr; c->inv_perm = nullptr;
+  }
+  gb_status st = gb_merge_frames_impl(ctx, (int)K, frames, poses, resolution, target, seed, out_xyzw, out_cov4x4, num_out, c);
+  if (st == GB_OK) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { gb_set_error("gb_merge_frames: %s", cudaGetErrorString(e)); st = GB_ERR_CUDA; }
+  }
+  if (st != GB_OK) { if (c) { if (c->base) cudaFree(c->base); delete c; } return st; }
+  if (out_cloud) *out_cloud = c;
+  return GB_OK;
 }
 
 extern "C" gb_status gb_preprocess_default_params(gb_preprocess_params* p) {

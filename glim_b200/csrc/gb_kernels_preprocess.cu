@@ -1127,3 +1127,181 @@ gb_status gb_find_neighbors_pyramid_impl(gb_ctx* ctx, size_t n_, const double* x
   GB_CUDA(cudaStreamSynchronize(st));
   return GB_OK;
 }
+
+// =============================================================================================
+// gb_merge_frames: gtsam_points::merge_frames(poses, frames, downsample_resolution, target_num_points) as SubMapping calls it
+// (src/glim/mapping/sub_mapping.cpp:481-497; the reference itself wanted merge_frames_gpu, commented out at :491): transform
+// the keyframe clouds into the submap origin frame (points q = R p + t, covariances R C R^T), voxel-grid average points AND
+// covariances at `downsample_resolution`, thin to `target_num_points` -- on the device, from the keyframes' device clouds.
+// The averaging is fp64 in (frame, original point index) order: bit-exact with the oracle (go_merge_frames) on the same fp32
+// inputs.  Thinning: the reference draws with std::mt19937; here the `target` voxels with the smallest hash(seed, voxel rank)
+// stay, in key order ([EXT], unpinned).
+// =============================================================================================
+namespace {
+
+struct MergeFrame { const float4* p0; const float4* p1; const float* p2; const int* inv_perm; int n; int offset; double T[12]; };
+
+__global__ void k_merge_transform(int num_frames, const MergeFrame* __restrict__ frames, int total, double4* __restrict__ pts, double* __restrict__ cov6) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  int f = 0;
+  while (f + 1 < num_frames && frames[f + 1].offset <= g) f++;
+  const MergeFrame& F = frames[f];
+  const int i = g - F.offset;
+  const int slot = F.inv_perm ? F.inv_perm[i] : i;
+  const float4 a0 = F.p0[slot];
+  const float4 a1 = F.p1[slot];
+  const float a2 = F.p2[slot];
+  const double* T = F.T;  // rows of the 3x4 pose
+  const double x = a0.x, y = a0.y, z = a0.z;
+  pts[g] = make_double4(T[0] * x + T[1] * y + T[2] * z + T[3], T[4] * x + T[5] * y + T[6] * z + T[7], T[8] * x + T[9] * y + T[10] * z + T[11], 1.0);
+  const double C[9] = {a0.w, a1.x, a1.y, a1.x, a1.z, a1.w, a1.y, a1.w, a2};
+  double RC[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) RC[r * 3 + c] = T[r * 4 + 0] * C[0 * 3 + c] + T[r * 4 + 1] * C[1 * 3 + c] + T[r * 4 + 2] * C[2 * 3 + c];
+  double* o = cov6 + 6 * (size_t)g;
+  int e = 0;
+  for (int r = 0; r < 3; r++)
+    for (int c = r; c < 3; c++) o[e++] = RC[r * 3 + 0] * T[c * 4 + 0] + RC[r * 3 + 1] * T[c * 4 + 1] + RC[r * 3 + 2] * T[c * 4 + 2];
+}
+__global__ void k_merge_means(const int* __restrict__ num_voxels, const int* __restrict__ starts, const int* __restrict__ idx, const double4* __restrict__ pts, const double* __restrict__ cov6,
+                              double4* __restrict__ o_pts, double* __restrict__ o_cov6) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= *num_voxels) return;
+  const int b = starts[v], e = starts[v + 1];
+  double s[4] = {0, 0, 0, 0}, c[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = b; k < e; k++) {
+    const int i = idx[k];
+    const double4 p = pts[i];
+    s[0] += p.x; s[1] += p.y; s[2] += p.z; s[3] += p.w;
+    for (int m = 0; m < 6; m++) c[m] += cov6[6 * (size_t)i + m];
+  }
+  const int cnt = e - b;
+  o_pts[v] = make_double4(s[0] / cnt, s[1] / cnt, s[2] / cnt, s[3] / cnt);
+  for (int m = 0; m < 6; m++) o_cov6[6 * (size_t)v + m] = c[m] / cnt;
+}
+__global__ void k_merge_hash_keys(int n_upper, const int* __restrict__ num_voxels, unsigned long long seed, unsigned long long* __restrict__ keys) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n_upper) keys[v] = v < *num_voxels ? rg_hash(seed, (unsigned)v) : ~0ull;
+}
+// keep flag per voxel (all, or the `target` smallest hashes), then an inclusive scan gives the output slot
+__global__ void k_merge_keep(int n_upper, const int* __restrict__ num_voxels, int target, const unsigned long long* __restrict__ sorted, unsigned long long seed, int* __restrict__ keep) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_upper) return;
+  int k = v < *num_voxels;
+  if (k && target > 0 && target < *num_voxels) k = rg_hash(seed, (unsigned)v) <= sorted[target - 1];
+  keep[v] = k;
+}
+__global__ void k_merge_emit(int n_upper, const int* __restrict__ keep, const int* __restrict__ pos, const double4* __restrict__ pts, const double* __restrict__ cov6, double4* __restrict__ o_pts, double* __restrict__ o_cov16,
+                             float4* __restrict__ s0, float4* __restrict__ s1, float* __restrict__ s2) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_upper || !keep[v]) return;
+  const int o = pos[v] - 1;
+  const double4 p = pts[v];
+  const double* c = cov6 + 6 * (size_t)v;
+  o_pts[o] = p;
+  double* C = o_cov16 + 16 * (size_t)o;
+  for (int e = 0; e < 16; e++) C[e] = 0.0;
+  C[0] = c[0]; C[4] = c[1]; C[8] = c[2]; C[1] = c[1]; C[5] = c[3]; C[9] = c[4]; C[2] = c[2]; C[6] = c[4]; C[10] = c[5];
+  s0[o] = make_float4((float)p.x, (float)p.y, (float)p.z, (float)c[0]);
+  s1[o] = make_float4((float)c[1], (float)c[2], (float)c[3], (float)c[4]);
+  s2[o] = (float)c[5];
+}
+
+}  // namespace
+
+gb_status gb_merge_frames_impl(gb_ctx* ctx, int K, const gb_cloud* const* frames, const double* poses, double resolution, int target, unsigned long long seed, double* out_xyzw, double* out_cov4x4, size_t* num_out, gb_cloud* cloud_out) {
+  cudaStream_t st = ctx->stream;
+  size_t total = 0;
+  std::vector<MergeFrame> mf((size_t)K);
+  for (int k = 0; k < K; k++) {
+    const gb_cloud* c = frames[k];
+    MergeFrame& F = mf[(size_t)k];
+    F.p0 = c->p0; F.p1 = c->p1; F.p2 = c->p2; F.inv_perm = c->inv_perm; F.n = (int)c->n; F.offset = (int)total;
+    for (int r = 0; r < 3; r++) for (int cc = 0; cc < 4; cc++) F.T[r * 4 + cc] = poses[(size_t)k * 16 + cc * 4 + r];
+    total += c->n;
+  }
+  *num_out = 0;
+  if (total == 0) return GB_OK;
+  const int n = (int)total;
+  const size_t N = total;
+  size_t cub_sort = 0, cub_scan = 0, cub_keys = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_sort, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, n, 0, 64, st);
+  cub::DeviceScan::InclusiveSum(nullptr, cub_scan, (int*)nullptr, (int*)nullptr, n, st);
+  cub::DeviceRadixSort::SortKeys(nullptr, cub_keys, (unsigned long long*)nullptr, (unsigned long long*)nullptr, n, 0, 64, st);
+  const size_t cub_b = align_up(std::max(std::max(cub_sort, cub_scan), cub_keys), 256);
+  const size_t planes = 2 * align_up(16 * N, 256) + align_up(4 * N, 256);
+  const size_t need = gb_cloud_reorder_scratch_bytes(N, planes) + cub_b + 256 + align_up(sizeof(MergeFrame) * (size_t)K, 256) + 2 * align_up(32 * N, 256) + 2 * align_up(48 * N, 256) + align_up(128 * N, 256)
+                      + 2 * align_up(8 * N, 256) + 6 * align_up(4 * (N + 1), 256) + 4096;
+  char* base = nullptr;
+  GB_CHECK(gb_ctx_scratch(ctx, need, (void**)&base));
+  Carver cv{base, 0};
+  char* staged = cv.take<char>(gb_cloud_reorder_scratch_bytes(N, planes));
+  void* d_cub = cv.take<char>(cub_b);
+  int* d_cnt = cv.take<int>(64);
+  MergeFrame* d_mf = cv.take<MergeFrame>((size_t)K);
+  double4* d_pts = cv.take<double4>(N);
+  double4* d_vpts = cv.take<double4>(N);
+  double* d_cov = cv.take<double>(6 * N);
+  double* d_vcov = cv.take<double>(6 * N);
+  double* d_ocov = cv.take<double>(16 * N);
+  unsigned long long* d_keys = cv.take<unsigned long long>(N);
+  unsigned long long* d_keys_s = cv.take<unsigned long long>(N);
+  int* d_idx = cv.take<int>(N + 1);
+  int* d_idx_s = cv.take<int>(N + 1);
+  int* d_flags = cv.take<int>(N + 1);
+  int* d_pos = cv.take<int>(N + 1);
+  int* d_starts = cv.take<int>(N + 1);
+  int* d_keep = cv.take<int>(N + 1);
+  void* h_mf = nullptr;
+  GB_CHECK(gb_ctx_pinned(ctx, sizeof(MergeFrame) * (size_t)K, &h_mf));
+  memcpy(h_mf, mf.data(), sizeof(MergeFrame) * (size_t)K);
+  GB_CUDA(cudaMemcpyAsync(d_mf, h_mf, sizeof(MergeFrame) * (size_t)K, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaMemsetAsync(d_cnt, 0, 256, st));
+  const int tb = 256, gb = (n + tb - 1) / tb;
+  k_merge_transform<<<gb, tb, 0, st>>>(K, d_mf, n, d_pts, d_cov);
+  k_grid_keys<<<gb, tb, 0, st>>>(n, d_pts, 1.0 / resolution, d_keys, d_idx);
+  size_t tmp = cub_b;
+  GB_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, tmp, d_keys, d_keys_s, d_idx, d_idx_s, n, 0, 64, st));
+  k_grid_flags<<<gb, tb, 0, st>>>(n, d_keys_s, d_flags);
+  tmp = cub_b;
+  GB_CUDA(cub::DeviceScan::InclusiveSum(d_cub, tmp, d_flags, d_pos, n, st));
+  k_copy_last_pos<<<1, 1, 0, st>>>(n, d_pos, d_cnt);  // V
+  k_grid_starts<<<gb, tb, 0, st>>>(n, d_keys_s, d_flags, d_pos, d_starts);
+  k_merge_means<<<(n + 127) / 128, 128, 0, st>>>(d_cnt, d_starts, d_idx_s, d_pts, d_cov, d_vpts, d_vcov);
+  // thinning to target_num_points
+  k_merge_hash_keys<<<gb, tb, 0, st>>>(n, d_cnt, seed, d_keys);
+  tmp = cub_b;
+  GB_CUDA(cub::DeviceRadixSort::SortKeys(d_cub, tmp, d_keys, d_keys_s, n, 0, 64, st));
+  k_merge_keep<<<gb, tb, 0, st>>>(n, d_cnt, target, d_keys_s, seed, d_keep);
+  tmp = cub_b;
+  GB_CUDA(cub::DeviceScan::InclusiveSum(d_cub, tmp, d_keep, d_pos, n, st));
+  int M = 0;
+  GB_CUDA(cudaMemcpyAsync(&M, d_pos + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  ctx->launches += 12;
+  *num_out = (size_t)M;
+  if (M == 0) return GB_OK;
+  const size_t c0 = align_up(16 * (size_t)M, 256), c2 = align_up(4 * (size_t)M, 256);
+  float4* s0 = (float4*)staged;
+  float4* s1 = (float4*)(staged + c0);
+  float* s2 = (float*)(staged + 2 * c0);
+  k_merge_emit<<<gb, tb, 0, st>>>(n, d_keep, d_pos, d_vpts, d_vcov, d_pts /* reused: emitted points */, d_ocov, s0, s1, s2);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  if (cloud_out) {
+    const size_t ctotal = 2 * c0 + c2;
+    const size_t bperm = align_up(sizeof(int) * (size_t)M, 256);
+    cloud_out->n = (size_t)M;
+    GB_CUDA(cudaMalloc(&cloud_out->base, ctotal + 2 * bperm));
+    cloud_out->bytes = ctotal + 2 * bperm;
+    char* d = (char*)cloud_out->base;
+    cloud_out->p0 = (float4*)d; cloud_out->p1 = (float4*)(d + c0); cloud_out->p2 = (float*)(d + 2 * c0); cloud_out->normals = nullptr;
+    cloud_out->perm = (int*)(d + ctotal); cloud_out->inv_perm = (int*)(d + ctotal + bperm);
+    GB_CHECK(gb_cloud_reorder_impl(ctx, cloud_out, staged, c0, c0, c2, 0));
+  }
+  if (out_xyzw) GB_CUDA(cudaMemcpyAsync(out_xyzw, d_pts, sizeof(double4) * (size_t)M, cudaMemcpyDeviceToHost, st));
+  if (out_cov4x4) GB_CUDA(cudaMemcpyAsync(out_cov4x4, d_ocov, sizeof(double) * 16 * (size_t)M, cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  return GB_OK;
+}

@@ -381,6 +381,25 @@ def overlap_gpu(voxelmaps, source: PointCloudGPU, deltas, ctx: Context | None = 
     return out.value
 
 
+def merge_frames_gpu(poses, frames, downsample_resolution: float, target_num_points: int = 0, seed: int = 0, ctx: Context | None = None, host_outputs: bool = True):
+    """gtsam_points::merge_frames(poses, frames, downsample_resolution, target_num_points) on the device (sub_mapping.cpp:481-497).
+    poses: K x (4,4) T_origin_frame; frames: K PointCloudGPU.  -> (points (M,4), covs (M,4,4) [i,row,col], PointCloudGPU)"""
+    ctx = ctx or frames[0].ctx
+    K = len(frames)
+    arr = (C.c_void_p * K)(*[f.h for f in frames])
+    T = pose16(np.stack([np.asarray(p, dtype=np.float64) for p in poses]))
+    cap = sum(f.n for f in frames)
+    pts = np.empty((cap, 4)) if host_outputs else None
+    cov = np.empty((cap, 16)) if host_outputs else None
+    m = C.c_size_t()
+    h = C.c_void_p()
+    check(lib().gb_merge_frames(ctx.h, K, C.cast(arr, C.c_void_p), ptr(T), float(downsample_resolution), int(target_num_points), int(seed), ptr(pts), ptr(cov), C.byref(m), C.byref(h)))
+    cloud = PointCloudGPU(ctx, h, m.value) if h.value else None
+    if not host_outputs:
+        return None, None, cloud
+    return pts[: m.value].copy(), cov[: m.value].reshape(-1, 4, 4).transpose(0, 2, 1).copy(), cloud
+
+
 overlap_auto = overlap_gpu  # gtsam_points::overlap_auto dispatches to the GPU version for GPU voxel maps (sub_mapping.cpp:252)
 
 

@@ -58,12 +58,17 @@ def run(env, args, metric_name):
     threads = bench.host_threads()
     ref = cpu_preprocess(pts, tms, params, threads)
     ok = bool(m == len(ref[0]) and np.array_equal(fr.points, ref[0]) and np.array_equal(np.sort(fr.neighbors.reshape(m, -1), axis=1), np.sort(ref[2], axis=1)) and np.allclose(covs, ref[4], atol=1e-9))
-    t_cpu = []
-    for _ in range(3):
-        tc = time.perf_counter()
-        cpu_preprocess(pts, tms, params, threads)
-        t_cpu.append(time.perf_counter() - tc)
-    cpu_ms = 1e3 * min(t_cpu)
+    # the strongest CPU number: best over thread counts (all threads is not the fastest on a 128-thread host) and repetitions
+    t_cpu = {}
+    for th in sorted({t for t in (2, 8, 16, 32, 64, threads) if t <= threads}):
+        best = 1e9
+        for _ in range(2):
+            tc = time.perf_counter()
+            cpu_preprocess(pts, tms, params, th)
+            best = min(best, time.perf_counter() - tc)
+        t_cpu[th] = best
+    threads = min(t_cpu, key=lambda t: t_cpu[t])
+    cpu_ms = 1e3 * t_cpu[threads]
     peaks = bench.load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # algorithmic bytes: raw point + time in (40 B), frame products out (point 32 + time 8 + k neighbours 4k + cov 128 + normal 32), device cloud planes (52 B)
@@ -78,7 +83,7 @@ def run(env, args, metric_name):
         "gpu_launches": int(launches), "clocks": None,
         "roofline": {"bound": "hbm", "achieved": alg / (per * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (per * 1e-3) / 1e9 / peak, "traffic": None,
                      "note": "a 60 k-point frame is ~20 short launches (sorts, scans, hash build, k-NN, covariances, reorder): launch- and latency-bound, far from the HBM roofline by construction"},
-        "cpu_baseline": {"value": n / (cpu_ms * 1e-3) / 1e6, "unit": "M raw points/s", "ms_per_frame": cpu_ms, "cores": threads, "kind": "port",
-                         "sample": "the same frame: oracle voxel grid + numpy gates / time sort + scipy cKDTree k-NN (all threads) + oracle covariance estimation (OpenMP, all threads); best of 3"},
+        "cpu_baseline": {"value": n / (cpu_ms * 1e-3) / 1e6, "unit": "M raw points/s", "ms_per_frame": cpu_ms, "cores": threads, "kind": "port", "ms_by_threads": {str(t): round(1e3 * v, 2) for t, v in t_cpu.items()},
+                         "sample": "the same frame: oracle voxel grid + numpy gates / time sort + scipy cKDTree k-NN (all threads) + oracle covariance estimation (OpenMP); best thread count, best of 2"},
         "speedup_vs_cpu": cpu_ms / per, "speedup_vs_cpu_e2e": cpu_ms / (ems / steps), "parity_check": {"ok": ok, "what": "points exact, neighbour sets exact, covariances 1e-9 vs the CPU pipeline"},
     }

@@ -240,6 +240,15 @@ typedef struct gb_preprocessed {
 GB_API gb_status gb_preprocess_default_params(gb_preprocess_params* params); /* config/config_preprocess.json + CloudPreprocessorParams defaults */
 GB_API gb_status gb_preprocess(gb_ctx* ctx, size_t n_raw, const double* xyzw, const double* times, const double* intensities, const gb_preprocess_params* params, gb_preprocessed* out);
 
+/* ---- gtsam_points::merge_frames(poses, frames, downsample_resolution, target_num_points) as SubMapping::create_submap calls
+ *      it (src/glim/mapping/sub_mapping.cpp:481-497; `merge_frames_gpu` is what the reference wanted at :491): transform the
+ *      keyframes' DEVICE clouds by T_origin_keyframe (points and covariances R C R^T), voxel-grid average points and
+ *      covariances, thin to target_num_points (<= 0: no thinning).  Outputs: the merged submap as a device cloud and / or as
+ *      host arrays (N x Vector4d, N x Matrix4d column-major, capacity = sum of the frames' sizes).  fp64 sums in
+ *      (frame, original point index) order. ---- */
+GB_API gb_status gb_merge_frames(gb_ctx* ctx, size_t num_frames, const gb_cloud* const* frames, const double* poses /* K x 16 */, double downsample_resolution, int target_num_points, uint64_t seed,
+                                 double* out_xyzw, double* out_cov4x4, size_t* num_out, gb_cloud** out_cloud);
+
 /* ---- glim::CloudDeskewing::deskew (src/glim/common/cloud_deskewing.cpp:11-55 constant velocity, :57-133 predicted IMU poses;
  *      called at src/glim/odometry/odometry_estimation_imu.cpp:313).  n_imu > 0: imu_times / imu_poses (n_imu x 16, T_world_imu)
  *      and `stamp` select the IMU-pose overload; n_imu == 0: linear_vel / angular_vel (either may be NULL = zero) select the

@@ -327,12 +327,57 @@ public:
     c->normals_gpu = static_cast<Vector3f*>(nr);
     return c;
   }
+  /// Wrap a device cloud that gb_preprocess / gb_merge_frames already built (takes ownership of `cloud`) together with an
+  /// owning copy of the matching host arrays: the frame looks exactly like the result of clone(), without the upload.
+  static Ptr adopt(const double* points4, const double* covs16, const double* normals4, const double* times, const double* intensities, std::size_t n, gb_cloud* cloud) {
+    Ptr c(new PointCloudGPU);
+    c->num_points = n;
+    if (points4) c->add_points(points4, n);
+    if (covs16) c->add_covs(covs16, n);
+    if (normals4) c->add_normals(normals4, n);
+    if (times) c->add_times(times, n);
+    if (intensities) c->add_intensities(intensities, n);
+    c->cloud_ = cloud;
+    if (cloud) {
+      void *p0 = nullptr, *p1 = nullptr, *nr = nullptr;
+      glim_b200::check(gb_cloud_device_ptrs(cloud, &p0, &p1, nullptr, &nr), "gb_cloud_device_ptrs");
+      c->points_gpu = static_cast<Vector3f*>(p0);
+      c->covs_gpu = covs16 ? static_cast<Matrix3f*>(p1) : nullptr;
+      c->normals_gpu = static_cast<Vector3f*>(nr);
+    }
+    return c;
+  }
   gb_cloud* handle() const { return cloud_; }
 
 private:
   PointCloudGPU() = default;
   gb_cloud* cloud_ = nullptr;
 };
+
+/// gtsam_points::merge_frames_gpu(poses, frames, downsample_resolution[, target_num_points]) -- the call the reference left
+/// commented out at src/glim/mapping/sub_mapping.cpp:491 (its CPU twin merge_frames is what :496 runs).  Frames must be
+/// PointCloudGPU; the merged submap comes back as a PointCloudGPU (host points / covariances + device cloud).
+inline PointCloudGPU::Ptr merge_frames_gpu(const std::vector<glim_b200::Pose>& poses, const std::vector<PointCloud::ConstPtr>& frames, double downsample_resolution, int target_num_points = 0, CUstream_st* stream = nullptr, std::uint64_t seed = 0) {
+  if (poses.size() != frames.size()) throw std::runtime_error("merge_frames_gpu: poses / frames size mismatch");
+  std::vector<const gb_cloud*> handles(frames.size());
+  std::vector<double> T(16 * frames.size());
+  std::size_t cap = 0;
+  for (std::size_t i = 0; i < frames.size(); i++) {
+    const auto* g = dynamic_cast<const PointCloudGPU*>(frames[i].get());
+    if (!g || !g->handle()) throw std::runtime_error("merge_frames_gpu: frames must be PointCloudGPU");
+    handles[i] = g->handle();
+    std::copy(poses[i].m.begin(), poses[i].m.end(), T.begin() + 16 * i);
+    cap += g->size();
+  }
+  std::vector<Vector4d> pts(cap);
+  std::vector<Matrix4d> covs(cap);
+  std::size_t m = 0;
+  gb_cloud* cloud = nullptr;
+  glim_b200::check(gb_merge_frames(glim_b200::Context::of_stream(stream), frames.size(), handles.data(), T.data(), downsample_resolution, target_num_points, seed, reinterpret_cast<double*>(pts.data()),
+                                   reinterpret_cast<double*>(covs.data()), &m, &cloud),
+                   "gb_merge_frames");
+  return PointCloudGPU::adopt(reinterpret_cast<const double*>(pts.data()), reinterpret_cast<const double*>(covs.data()), nullptr, nullptr, nullptr, m, cloud);
+}
 
 struct VoxelMapInfo {
   int num_voxels = 0;

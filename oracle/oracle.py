@@ -63,6 +63,8 @@ def lib():
         L.go_knn_bruteforce.argtypes = [i32, vp, i32, i32, vp, vp]
         L.go_voxelgrid_sampling.restype = i32
         L.go_voxelgrid_sampling.argtypes = [i32, vp, vp, vp, f64, vp, vp, vp]
+        L.go_merge_frames.restype = i32
+        L.go_merge_frames.argtypes = [i32, vp, vp, vp, vp, f64, i32, C.c_uint64, vp, vp]
         L.go_randomgrid_sampling.restype = i32
         L.go_randomgrid_sampling.argtypes = [i32, vp, f64, f64, C.c_uint64, vp]
         L.go_deskew_const_vel.restype = i32
@@ -276,6 +278,18 @@ def voxelgrid_sampling(pts4, resolution, times=None, intensities=None):
     oi = np.empty((n,)) if it is not None else None
     m = lib().go_voxelgrid_sampling(n, _p(pts4), _p(t), _p(it), float(resolution), _p(op), _p(ot), _p(oi))
     return op[:m].copy(), (ot[:m].copy() if ot is not None else None), (oi[:m].copy() if oi is not None else None)
+
+
+def merge_frames(poses, clouds, resolution, target=0, seed=0):
+    """clouds: list of (xyz f32 (n,3), cov6 f32 (n,6)) device-layout clouds; poses: list of 4x4.  -> points (M,4), covs (M,4,4) [i,row,col]"""
+    n = np.array([len(c[0]) for c in clouds], np.int32)
+    xyz = _f32(np.concatenate([c[0] for c in clouds]))
+    cov6 = _f32(np.concatenate([c[1] for c in clouds]))
+    T = np.concatenate([pose_colmajor(p) for p in poses])
+    tot = int(n.sum())
+    op, oc = np.empty((tot, 4)), np.empty((tot, 16))
+    m = lib().go_merge_frames(len(clouds), _p(n), _p(xyz), _p(cov6), _p(T), float(resolution), int(target), int(seed), _p(op), _p(oc))
+    return op[:m].copy(), oc[:m].reshape(m, 4, 4).transpose(0, 2, 1).copy()
 
 
 def randomgrid_sampling(pts4, resolution, rate, seed=0):

@@ -27,6 +27,7 @@ def test_shims_compile_standalone_and_gtsam_mode(tmp_path):
     subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{INC}", "-c", os.path.join(CPP, "shim_main.cpp"), "-o", str(tmp_path / "a.o")])
     subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{INC}", f"-I{os.path.join(CPP, 'gtsam_stub')}", "-c", os.path.join(CPP, "gtsam_mode_check.cpp"), "-o", str(tmp_path / "b.o")])
     subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-pthread", f"-I{INC}", "-c", os.path.join(CPP, "replay_glim.cpp"), "-o", str(tmp_path / "c.o")])
+    subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{INC}", "-c", os.path.join(CPP, "preprocess_main.cpp"), "-o", str(tmp_path / "d.o")])
 
 
 def test_solver_handoff_blocks_host_only():
@@ -149,3 +150,48 @@ def test_replay_glim_modules_across_threads_under_asan(tmp_path):
                 assert util.rel_err(got[k], ref[k]) < util.REL_TOL
         if level == 1:
             assert ov[0] == ov[1] == ov[2] == oracle.overlap_gpumap([m], xyz1, [delta])
+
+
+@pytest.mark.gpu
+def test_cpp_preprocess_shims_match_oracle(tmp_path):
+    """glim::CloudPreprocessor / CloudCovarianceEstimation shims (C++, include/glim_b200/glim_preprocess_compat.hpp) and the
+    fused preprocess_to_gpu_frame against the oracle composition of the reference pipeline; merge_frames_gpu on the result."""
+    from glim_b200 import capi, synth
+    from oracle import oracle
+
+    exe = tmp_path / "preprocess_main"
+    libdir = os.path.dirname(capi.SO_PATH)
+    subprocess.check_call([GXX, "-std=c++17", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", f"-I{INC}", os.path.join(CPP, "preprocess_main.cpp"), "-o", str(exe), f"-L{libdir}", "-lglim_b200", f"-Wl,-rpath,{libdir}"])
+    sc = synth.make_hall_scene()
+    P, T = synth.scan(sc, "hdl32", synth.arc_trajectory(8)[2], synth.rng_for(43), n_rays=32 * 500)
+    k, res, near, far = 10, 0.2, 1.0, 60.0
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        np.array([len(P)], np.int32).tofile(f)
+        np.ascontiguousarray(P).tofile(f)
+        np.ascontiguousarray(T).tofile(f)
+        np.array([res, near, far]).tofile(f)
+        np.array([k], np.int32).tofile(f)
+    env = dict(os.environ, ASAN_OPTIONS="protect_shadow_gap=0:detect_leaks=0")
+    r = subprocess.run([str(exe), str(inp), str(out)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
+    raw = open(out, "rb").read()
+    m = int(np.frombuffer(raw[:4], np.int32)[0])
+    o = 4
+    pts = np.frombuffer(raw[o : o + 32 * m], np.float64).reshape(m, 4); o += 32 * m
+    tms = np.frombuffer(raw[o : o + 8 * m], np.float64); o += 8 * m
+    nb = np.frombuffer(raw[o : o + 4 * m * k], np.int32).reshape(m, k); o += 4 * m * k
+    cov_a = np.frombuffer(raw[o : o + 128 * m], np.float64).reshape(m, 4, 4).transpose(0, 2, 1); o += 128 * m
+    cov_b = np.frombuffer(raw[o : o + 128 * m], np.float64).reshape(m, 4, 4).transpose(0, 2, 1); o += 128 * m
+    merged, has_gpu = np.frombuffer(raw[o : o + 8], np.int32)
+    rp, rt, _ = oracle.voxelgrid_sampling(P, res, times=T)
+    sq = (rp[:, :3] ** 2).sum(1)
+    idx = np.nonzero((sq > near * near) & (sq < far * far))[0]
+    idx = idx[np.argsort(rt[idx], kind="stable")]
+    rp, rt = np.ascontiguousarray(rp[idx]), rt[idx]
+    assert m == len(rp) and np.array_equal(pts, rp) and np.array_equal(tms, rt)
+    rnb, _ = oracle.knn_bruteforce(rp, k)
+    assert np.array_equal(nb, rnb)
+    _, rc = oracle.covariance_estimate(rp, rnb)
+    assert np.allclose(cov_a, rc, atol=1e-9) and np.allclose(cov_b, rc, atol=1e-9)
+    assert has_gpu == 1 and 0 < merged <= 2 * m

@@ -564,3 +564,34 @@ def test_pyramid_knn_is_exact_on_hard_clouds(ctx, monkeypatch):
             nb = preprocess.find_neighbors(cloud, k, ctx=ctx).reshape(len(cloud), k)
             ref, _ = oracle.knn_bruteforce(cloud, k)
             assert np.array_equal(nb, ref)
+
+
+def test_merge_frames_gpu_matches_oracle(ctx):
+    """SURVEY 8(f) row 3 -- gtsam_points::merge_frames as SubMapping::create_submap calls it (sub_mapping.cpp:481-497): five
+    keyframe clouds transformed into the submap origin frame, voxel-grid averaged (points and covariances), thinned to a target
+    size.  fp64 sums in the same order as the oracle: bit-exact; the device cloud is the fp32 cast of the host product."""
+    sc = synth.make_hall_scene()
+    traj = synth.arc_trajectory(8, step=1.5)
+    clouds, packed, poses = [], [], []
+    origin = traj[2]
+    for i in range(5):
+        pts, _ = synth.scan(sc, "hdl32", traj[i], synth.rng_for(61, i), n_rays=32 * 250)
+        _, cov = synth.with_covariances(pts, 10)
+        clouds.append(gpu.PointCloudGPU.clone(pts, cov, ctx=ctx))
+        packed.append(oracle.pack_cloud(pts, util.cov_colmajor16(cov)))
+        poses.append(synth.inv_pose(origin) @ traj[i])
+    for target in (0, 3000):
+        pts, covs, merged = gpu.merge_frames_gpu(poses, clouds, 0.25, target, seed=9, ctx=ctx)
+        rp, rc = oracle.merge_frames(poses, packed, 0.25, target, seed=9)
+        assert len(pts) == len(rp) and (target == 0 or len(pts) == target)
+        assert np.array_equal(pts, rp) and np.array_equal(covs, rc)
+        gx, gc = merged.download()
+        xyz, cov6 = oracle.pack_cloud(pts, util.cov_colmajor16(covs))
+        assert np.array_equal(gx, xyz) and np.array_equal(gc, cov6)
+        # covariances stay symmetric PSD with zero last row / column (the invariants SubMap::load checks, sub_map.cpp:151-166)
+        assert np.allclose(covs, covs.transpose(0, 2, 1)) and not covs[:, 3, :].any() and not covs[:, :, 3].any()
+        assert np.linalg.eigvalsh(covs[:, :3, :3]).min() > 0
+    # the merged submap is a valid VGICP target / source
+    m = gpu.GaussianVoxelMapGPU(0.5, ctx=ctx).insert(merged)
+    got = gpu.IntegratedVGICPFactorGPU(np.eye(4), 1, m, merged, ctx=ctx).linearize({1: np.eye(4)})
+    assert got["num_inliers"] == merged.size()
