@@ -483,9 +483,7 @@ def measure_simple(env, name, w, steps, warmup):
 
     def step_e2e():
         for sw in sweeps:
-            sw.set_poses(sw._deltas)
-            sw.launch()
-            sw.fetch()
+            sw.linearize(sw._deltas)  # gb_sweep_linearize: poses H2D + launch + records D2H (one CUDA-graph launch for small sweeps)
 
     for _ in range(3):
         step_e2e()
@@ -525,7 +523,7 @@ def parity_check(env, w, fset, peers_row_fetch, K, seed=7):
                     packed[c] = oracle.pack_cloud(w.host_clouds[c][0], c16(w.host_clouds[c][1]))
             if (f.target, f.level) not in maps:
                 maps[(f.target, f.level)] = oracle.GpuMap(*packed[f.target], w.resolutions[f.level])
-            ref, _ = oracle.linearize_gpumap(maps[(f.target, f.level)], *packed[f.source], fset.deltas[k])
+            ref, _ = oracle.linearize_gpumap(maps[(f.target, f.level)], *packed[f.source], fset.deltas[k], normals=w.host_normals[f.source] if w.surface_validation else None)
             tot += ref
         ref = oracle.split122(tot)
         got = multi_gpu.unpack_slab_row(rows[pair])
@@ -698,6 +696,9 @@ def main():
 
     def step_e2e():
         for k, (sw, slab, ps) in enumerate(zip(sweeps, slabs, peers)):
+            if ps is None and slab is None:
+                sw.linearize(host_deltas[k])  # gb_sweep_linearize: poses H2D + launch + records D2H (one CUDA-graph launch for small sweeps)
+                continue
             sw.set_poses(host_deltas[k])  # gb_sweep_set_poses: pinned staging + H2D (double buffered, no stream sync)
             if ps is not None:
                 sw.launch()
@@ -711,9 +712,6 @@ def main():
                     dist.all_reduce(slab, op=dist.ReduceOp.SUM)
                 host_slabs[k].copy_(slab, non_blocking=True)
                 ctx.synchronize()
-            else:
-                sw.launch()
-                sw.fetch()  # gb_sweep_fetch: D2H of the gb_linearized6 records + stream sync
 
     for _ in range(3):
         step_e2e()

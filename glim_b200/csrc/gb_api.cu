@@ -320,6 +320,8 @@ extern "C" gb_status gb_vgicp_factor_create(gb_ctx* ctx, const gb_voxelmap* targ
   // clouds / voxel maps may have been uploaded through another context (another module thread): device memory is shared,
   // and every producer call returns only after its stream has drained, so only the DEVICE has to match
   GB_REQUIRE(target->device == ctx->device && source->device == ctx->device, "cloud / voxel map live on another device");
+  if (flags & GB_FACTOR_SURFACE_VALIDATION)
+    GB_REQUIRE(source->normals != nullptr, "surface validation needs the source frame's normals on the device (PointCloudGPU::clone of a frame that has normals)");
   gb_factor* f = new (std::nothrow) gb_factor();
   if (!f) return GB_ERR_INTERNAL;
   f->ctx = ctx; f->target = target; f->source = source; f->flags = flags; f->single = nullptr; f->inlier_frac = -1.f; f->id = g_next_factor_id.fetch_add(1);
@@ -368,6 +370,7 @@ static void sweep_free(gb_sweep* s) {
       }
     }
     for (int k = 0; k < 2; k++) if (s->pose_ev[k]) cudaEventDestroy(s->pose_ev[k]);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     if (s->d_pair_ptr) cudaFree(s->d_pair_ptr);
     pool_put(ctx, s->pool_d, s->pool_d_cap, s->pool_h, s->pool_h_cap);
     delete s;
@@ -473,6 +476,8 @@ static gb_status sweep_learn_inliers(gb_sweep* s) {
   GB_CUDA(cudaMemcpyAsync(s->d_tiles, s->h_tiles, sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, s->ctx->stream));
   s->num_tiles = (int)tiles.size();
   s->grid = std::max(1, std::min((s->num_tiles + 7) / 8, s->capacity));
+  if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+  if (s->graph_state == 1) s->graph_state = 0;  // the launch geometry changed: capture again
   return GB_OK;
 }
 
@@ -500,6 +505,7 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
   s->num_tiles = 0; s->point_factors = 0; s->algorithmic_bytes = 0; s->key = 0; s->stale = false;
   s->h_pose_slot[0] = s->h_pose_slot[1] = nullptr; s->pose_ev[0] = s->pose_ev[1] = nullptr; s->pose_slot = 0;
   s->pool_d = nullptr; s->pool_d_cap = 0; s->pool_h = nullptr; s->pool_h_cap = 0;
+  s->graph_exec = nullptr; s->graph_state = 0;
 
   // kernel generation and work-item policy
   // Kernel policy (measured on B200, profiles/r02_ab_kernels.txt): small sweeps -- about one item per warp: an odometry
@@ -532,10 +538,14 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
 
   std::vector<FactorDesc> descs(F);
   std::vector<int2> tiles;
+  bool any_sv = false;
   for (size_t f = 0; f < F; f++) {
     const gb_factor* fa = factors[f];
     FactorDesc& D = descs[f];
     D.p0 = fa->source->p0; D.p1 = fa->source->p1; D.p2 = fa->source->p2;
+    const bool sv = (fa->flags & GB_FACTOR_SURFACE_VALIDATION) != 0;
+    D.normals = sv ? fa->source->normals : nullptr;
+    any_sv = any_sv || sv;
     D.buckets = fa->target->buckets; D.voxels = fa->target->voxels;
     D.mask = (uint32_t)fa->target->num_buckets - 1u;
     D.max_scan = fa->target->max_scan;
@@ -551,8 +561,9 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     // our deliberately sparse table (>= 8 V): padding we added for speed must not inflate the achieved-GB/s figure.
     uint64_t nb_ref = 16384;
     while (nb_ref < (uint64_t)fa->target->num_voxels) nb_ref *= 2;
-    s->algorithmic_bytes += (uint64_t)D.n * 48 + (uint64_t)fa->target->num_voxels * 48 + nb_ref * 16 + 64 + 488;
+    s->algorithmic_bytes += (uint64_t)D.n * (48 + (sv ? 12 : 0)) + (uint64_t)fa->target->num_voxels * 48 + nb_ref * 16 + 64 + 488;  // +12 B / point: the normals, when they are read
   }
+  if (any_sv && s->kernel_version == 4) s->kernel_version = s->strided ? 5 : 3;  // the staged experiment does not carry normals
   build_items(s, descs.data(), tiles);
   s->num_tiles = (int)tiles.size();
   s->grid = std::max(1, std::min((s->num_tiles + 7) / 8, s->capacity));
@@ -691,10 +702,65 @@ static gb_status cached_sweep(gb_ctx* ctx, size_t F, gb_factor* const* factors, 
   gb_sweep* s = nullptr;
   GB_CHECK(gb_sweep_create(ctx, F, factors, nullptr, &s));
   s->key = key;
-  if (ctx->sweep_cache.size() >= 8) { sweep_free(ctx->sweep_cache.front()); ctx->sweep_cache.erase(ctx->sweep_cache.begin()); }
+  if (ctx->sweep_cache.size() >= 64) { sweep_free(ctx->sweep_cache.front()); ctx->sweep_cache.erase(ctx->sweep_cache.begin()); }
   ctx->sweep_cache.push_back(s);
   *out = s;
   return GB_OK;
+}
+
+// A small sweep (one wave, no queue, no exchange) has a fixed topology: poses H2D -> kernel -> records D2H.  Captured once
+// as a CUDA graph, every linearization is then ONE launch call instead of three API calls (the online odometry path calls this
+// ~10 times per frame: odometry_estimation_gpu.cpp:383-386).
+static bool graph_eligible(const gb_sweep* s) {
+  static const bool enabled = env_int("GB_GRAPH", 1) != 0;
+  return enabled && s->graph_state >= 0 && s->strided && !s->peer && !s->d_slab && (unsigned long long)s->num_tiles <= (unsigned long long)s->grid * 8ull && s->F > 0;
+}
+static gb_status sweep_linearize(gb_sweep* s, const double* T, gb_linearized6* out) {
+  if (!graph_eligible(s)) {
+    GB_CHECK(gb_sweep_set_poses(s, T));
+    GB_CHECK(sweep_launch(s, GB_MODE_LINEARIZE));
+    return gb_sweep_fetch(s, out);
+  }
+  if (s->stale) { gb_set_error("a factor of this sweep has been destroyed"); return GB_ERR_INVALID_ARGUMENT; }
+  gb_ctx* ctx = s->ctx;
+  GB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t pose_bytes = sizeof(double) * 16 * s->F, out_bytes = sizeof(double) * GB_OUT_DOUBLES * s->F;
+  if (s->graph_state == 0) {
+    GB_CUDA(cudaStreamSynchronize(st));  // nothing of this sweep may be in flight while its work is captured
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      ok = cudaMemcpyAsync(s->d_poses, s->h_pose_slot[0], pose_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+      const uint64_t launches = ctx->launches;
+      ok = ok && gb_launch_sweep(s, GB_MODE_LINEARIZE) == GB_OK;
+      ctx->launches = launches;  // counted per graph launch below
+      ok = ok && cudaMemcpyAsync(s->h_out, s->d_out, out_bytes, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+      ok = (cudaStreamEndCapture(st, &graph) == cudaSuccess) && ok && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&s->graph_exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      s->graph_exec = nullptr;
+      s->graph_state = -1;
+      return sweep_linearize(s, T, out);  // plain launches from now on
+    }
+    s->graph_state = 1;
+  }
+  memcpy(s->h_pose_slot[0], T, pose_bytes);  // the previous graph launch was synchronised below: the slot is free
+  GB_CUDA(cudaGraphLaunch(s->graph_exec, st));
+  ctx->launches++;
+  GB_CUDA(cudaStreamSynchronize(st));
+  memcpy(out, s->h_out, out_bytes);
+  return sweep_learn_inliers(s);
+}
+
+extern "C" gb_status gb_sweep_linearize(gb_sweep* s, const double* T, gb_linearized6* out) {
+  GB_REQUIRE(s && (s->F == 0 || (T && out)), "null argument");
+  if (s->F == 0) return GB_OK;
+  GB_LOCK(s->ctx);
+  return sweep_linearize(s, T, out);
 }
 
 extern "C" gb_status gb_factor_set_linearize(gb_ctx* ctx, size_t F, gb_factor* const* factors, const double* T, gb_linearized6* out) {
@@ -704,9 +770,7 @@ extern "C" gb_status gb_factor_set_linearize(gb_ctx* ctx, size_t F, gb_factor* c
   GB_LOCK(ctx);
   gb_sweep* s = nullptr;
   GB_CHECK(cached_sweep(ctx, F, factors, &s));
-  GB_CHECK(gb_sweep_set_poses(s, T));
-  GB_CHECK(sweep_launch(s, GB_MODE_LINEARIZE));
-  return gb_sweep_fetch(s, out);
+  return sweep_linearize(s, T, out);
 }
 
 extern "C" gb_status gb_factor_set_error(gb_ctx* ctx, size_t F, gb_factor* const* factors, const double* T_lin, const double* T_eval, double* errors) {
@@ -735,9 +799,7 @@ extern "C" gb_status gb_vgicp_linearize(gb_factor* f, const double T[16], gb_lin
   GB_LOCK(f->ctx);
   gb_sweep* s = nullptr;
   GB_CHECK(single_sweep(f, &s));
-  GB_CHECK(gb_sweep_set_poses(s, T));
-  GB_CHECK(sweep_launch(s, GB_MODE_LINEARIZE));
-  return gb_sweep_fetch(s, out);
+  return sweep_linearize(s, T, out);
 }
 extern "C" gb_status gb_vgicp_error(gb_factor* f, const double T_lin[16], const double T_eval[16], double* error) {
   GB_REQUIRE(f && T_lin && T_eval && error, "null argument");

@@ -69,11 +69,12 @@ struct gb_voxelmap {
   size_t bytes;
 };
 
-// device-side factor descriptor (72 B)
+// device-side factor descriptor (80 B)
 struct FactorDesc {
   const float4* p0;
   const float4* p1;
   const float* p2;
+  const float4* normals;  // source normals, non-null only when surface validation is on for this factor
   const int4* buckets;
   const float4* voxels;
   uint32_t mask;
@@ -85,7 +86,7 @@ struct FactorDesc {
   int num_tiles;
   int first_tile;
 };
-static_assert(sizeof(FactorDesc) == 72, "FactorDesc size");
+static_assert(sizeof(FactorDesc) == 80, "FactorDesc size");
 
 struct gb_factor {
   gb_ctx* ctx;
@@ -167,6 +168,8 @@ struct gb_sweep {
   double* h_pose_slot[2]; // pinned pose staging, double buffered (no stream sync in gb_sweep_set_poses)
   cudaEvent_t pose_ev[2]; // recorded after the H2D that read the slot
   int pose_slot;
+  cudaGraphExec_t graph_exec;       // small sweeps: poses H2D -> kernel -> records D2H as ONE graph launch (gb_factor_set_linearize)
+  int graph_state;                  // 0 = not built, 1 = valid, -1 = capture failed (plain launches from then on)
   void* pool_d; size_t pool_d_cap;  // the blocks this sweep took from its context's pool
   void* pool_h; size_t pool_h_cap;
 };

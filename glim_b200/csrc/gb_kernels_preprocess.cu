@@ -1153,16 +1153,19 @@ __global__ void k_merge_transform(int num_frames, const MergeFrame* __restrict__
   const float4 a1 = F.p1[slot];
   const float a2 = F.p2[slot];
   const double* T = F.T;  // rows of the 3x4 pose
+  // un-contracted fp64 with a fixed association order: bit-exact with the oracle (go_merge_frames, built with fp-contract=off)
   const double x = a0.x, y = a0.y, z = a0.z;
-  pts[g] = make_double4(T[0] * x + T[1] * y + T[2] * z + T[3], T[4] * x + T[5] * y + T[6] * z + T[7], T[8] * x + T[9] * y + T[10] * z + T[11], 1.0);
+  double q[3];
+  for (int r = 0; r < 3; r++) q[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[r * 4 + 0], x), __dmul_rn(T[r * 4 + 1], y)), __dmul_rn(T[r * 4 + 2], z)), T[r * 4 + 3]);
+  pts[g] = make_double4(q[0], q[1], q[2], 1.0);
   const double C[9] = {a0.w, a1.x, a1.y, a1.x, a1.z, a1.w, a1.y, a1.w, a2};
   double RC[9];
   for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++) RC[r * 3 + c] = T[r * 4 + 0] * C[0 * 3 + c] + T[r * 4 + 1] * C[1 * 3 + c] + T[r * 4 + 2] * C[2 * 3 + c];
+    for (int c = 0; c < 3; c++) RC[r * 3 + c] = __dadd_rn(__dadd_rn(__dmul_rn(T[r * 4 + 0], C[0 * 3 + c]), __dmul_rn(T[r * 4 + 1], C[1 * 3 + c])), __dmul_rn(T[r * 4 + 2], C[2 * 3 + c]));
   double* o = cov6 + 6 * (size_t)g;
   int e = 0;
   for (int r = 0; r < 3; r++)
-    for (int c = r; c < 3; c++) o[e++] = RC[r * 3 + 0] * T[c * 4 + 0] + RC[r * 3 + 1] * T[c * 4 + 1] + RC[r * 3 + 2] * T[c * 4 + 2];
+    for (int c = r; c < 3; c++) o[e++] = __dadd_rn(__dadd_rn(__dmul_rn(RC[r * 3 + 0], T[c * 4 + 0]), __dmul_rn(RC[r * 3 + 1], T[c * 4 + 1])), __dmul_rn(RC[r * 3 + 2], T[c * 4 + 2]));
 }
 __global__ void k_merge_means(const int* __restrict__ num_voxels, const int* __restrict__ starts, const int* __restrict__ idx, const double4* __restrict__ pts, const double* __restrict__ cov6,
                               double4* __restrict__ o_pts, double* __restrict__ o_cov6) {

@@ -141,6 +141,25 @@ __device__ __forceinline__ void accumulate_hit(float (&acc)[32], const PoseF& Pe
   }
 }
 
+// Surface validation (set_enable_surface_validation(true), odometry_estimation_gpu.cpp:145, :162).  The reference rule lives
+// in the un-vendored gtsam_points and is not recoverable here: ours is an ORIENTATION-CONSISTENCY gate that needs
+// no eigen-decomposition.  With n = R n_A (source normal, flipped towards the sensor by the covariance estimator, rotated into
+// the target frame) a correspondence is kept iff   3 n^T C_B n <= tr(C_B),
+// i.e. the voxel's spread along the source normal is at most its mean spread: for a planar voxel with normal m this is
+// |n . m| >= 1/sqrt(3) (within ~55 degrees); voxels that mix surfaces (corners, thin walls seen from both sides) or face
+// another way are rejected.  Canonical fp32 operation order (the oracle evaluates the same expression bit for bit).
+__device__ __forceinline__ bool surface_ok(const PoseF& P, const float4 nr, float bxx, float bxy, float bxz, float byy, float byz, float bzz) {
+  const float nx = fmaf(P.r00, nr.x, fmaf(P.r01, nr.y, P.r02 * nr.z));
+  const float ny = fmaf(P.r10, nr.x, fmaf(P.r11, nr.y, P.r12 * nr.z));
+  const float nz = fmaf(P.r20, nr.x, fmaf(P.r21, nr.y, P.r22 * nr.z));
+  const float ux = fmaf(bxx, nx, fmaf(bxy, ny, bxz * nz));
+  const float uy = fmaf(bxy, nx, fmaf(byy, ny, byz * nz));
+  const float uz = fmaf(bxz, nx, fmaf(byz, ny, bzz * nz));
+  const float s = fmaf(nx, ux, fmaf(ny, uy, nz * uz));
+  const float tr = (bxx + byy) + bzz;
+  return 3.0f * s <= tr;
+}
+
 // probe result of one point given its first two buckets (b, b1 fetched together: adjacent 16-byte slots, one round trip)
 __device__ __forceinline__ int resolve_probe(const FactorDesc& D, const int4 b, const int4 b1, uint32_t h, int cx, int cy, int cz) {
   int v = -1;
@@ -709,7 +728,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep3(
         const float4 v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]);
         const float4 v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]);
         const float4 v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
-        accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
+        if (D.normals == nullptr || surface_ok(P, __ldg(&D.normals[i]), v0.w, v1.x, v1.y, v1.z, v1.w, v2.x)) accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
       }
       __syncwarp();  // the queue is overwritten by the next round
     }
@@ -898,14 +917,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep5(
           const float4 v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]);
           const float4 v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]);
           const float4 v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
-          accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
+          if (D.normals == nullptr || surface_ok(P, __ldg(&D.normals[e.x]), v0.w, v1.x, v1.y, v1.z, v1.w, v2.x)) accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
         }
       } else {  // software pipelined: the lane's next hit is in flight while the current one is processed
         int k = lane;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, v0 = a0, v1 = a0, v2 = a0;
         float a2 = 0.f;
+        unsigned cur_i = 0;
         if (k < nq) {
           const uint2 e = q[k];
+          cur_i = e.x;
           a0 = __ldg(&D.p0[e.x]); a1 = __ldg(&D.p1[e.x]); a2 = __ldg(&D.p2[e.x]);
           v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]); v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]); v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
         }
@@ -914,13 +935,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep5(
           const int kn = k + 32;
           float4 na0 = a0, na1 = a1, nv0 = v0, nv1 = v1, nv2 = v2;
           float na2 = a2;
+          unsigned next_i = cur_i;
           if (kn < nq) {
             const uint2 e = q[kn];
+            next_i = e.x;
             na0 = __ldg(&D.p0[e.x]); na1 = __ldg(&D.p1[e.x]); na2 = __ldg(&D.p2[e.x]);
             nv0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]); nv1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]); nv2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
           }
-          accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
+          if (D.normals == nullptr || surface_ok(P, __ldg(&D.normals[cur_i]), v0.w, v1.x, v1.y, v1.z, v1.w, v2.x)) accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
           a0 = na0; a1 = na1; a2 = na2; v0 = nv0; v1 = nv1; v2 = nv2;
+          cur_i = next_i;
           k = kn;
         }
       }

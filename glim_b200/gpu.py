@@ -313,6 +313,13 @@ class Sweep:
         check(lib().gb_sweep_fetch(self.h, ptr(out)))
         return out
 
+    def linearize(self, deltas) -> np.ndarray:
+        """gb_sweep_linearize: poses up, one launch (a CUDA graph for small sweeps), records down."""
+        out = np.zeros(self.F, LIN_DTYPE)
+        self._poses = pose16(deltas)
+        check(lib().gb_sweep_linearize(self.h, ptr(self._poses), ptr(out)))
+        return out
+
     def results_device_ptr(self) -> int:
         p = C.c_void_p()
         check(lib().gb_sweep_results_device(self.h, C.byref(p)))

@@ -47,6 +47,8 @@ class Workload:
         self.name = name
         self.ctx = ctx
         self.host_clouds: list = []  # (points (N,4), covs (N,4,4))
+        self.host_normals: list = []  # (N,4) per cloud (only the workloads whose factors use surface validation fill it)
+        self.surface_validation = False  # factor->set_enable_surface_validation(true): odometry only (odometry_estimation_gpu.cpp:145, :162)
         self.poses: list = []  # ground-truth T_world_sensor per cloud
         self.resolutions: list = []  # voxel resolution per level
         self.clouds: list = []  # gpu.PointCloudGPU
@@ -59,8 +61,9 @@ class Workload:
     def upload(self):
         if self.ctx is None:  # host-only construction (CPU tests, reference arm without a GPU)
             return
-        for pts, cov in self.host_clouds:
-            self.clouds.append(gpu.PointCloudGPU.clone(pts, cov, ctx=self.ctx))
+        for k, (pts, cov) in enumerate(self.host_clouds):
+            nrm = self.host_normals[k] if k < len(self.host_normals) else None
+            self.clouds.append(gpu.PointCloudGPU.clone(pts, cov, nrm, ctx=self.ctx))
 
     def overlap(self, targets, level, source, deltas) -> float:
         """overlap_gpu(voxelmaps, source, deltas): GPU kernel when a context exists, else a host numpy twin of the
@@ -95,6 +98,8 @@ class Workload:
         out = []
         for f in fset.factors:
             g = gpu.IntegratedVGICPFactorGPU(f.target, f.source, self.maps[f.target][f.level], self.clouds[f.source], ctx=self.ctx)
+            if self.surface_validation:
+                g.set_enable_surface_validation(True)
             out.append(g)
         return out
 
@@ -128,12 +133,14 @@ def _covariances(points, k, ctx, use_gpu):
     return synth.with_covariances(points, k)
 
 
-def make_scan(scene, sensor, T, rng, n_rays=None, max_points=None, ctx=None, use_gpu=False):
+def make_scan(scene, sensor, T, rng, n_rays=None, max_points=None, ctx=None, use_gpu=False, with_normals=False):
     pts, tms = synth.scan(scene, sensor, T, rng, n_rays=n_rays, backend="torch" if (use_gpu and ctx is not None) else "numpy")
     if max_points is not None and len(pts) > max_points:
         sel = np.sort(rng.choice(len(pts), max_points, replace=False))  # random_sampling keeps the order (sub_mapping.cpp:385)
         pts, tms = pts[sel], tms[sel]
-    _, cov = _covariances(pts, 10, ctx, use_gpu)
+    nrm, cov = _covariances(pts, 10, ctx, use_gpu)
+    if with_normals:
+        return np.ascontiguousarray(pts), np.ascontiguousarray(cov), np.ascontiguousarray(nrm)
     return np.ascontiguousarray(pts), np.ascontiguousarray(cov)
 
 
@@ -182,8 +189,12 @@ def odometry_stream(ctx, n_frames=64, first_bench_frame=16, sensor="hdl32", n_ra
     sc = synth.make_hall_scene()
     traj = synth.arc_trajectory(n_frames, step=step)
     rng_pose = synth.rng_for(202)
+    w.surface_validation = True  # odometry_estimation_gpu.cpp:145, :162
+    w.notes["surface_validation"] = True
     for i in range(n_frames):
-        w.host_clouds.append(make_scan(sc, sensor, traj[i], synth.rng_for(201, i), n_rays=n_rays, ctx=ctx, use_gpu=use_gpu))
+        pts, cov, nrm = make_scan(sc, sensor, traj[i], synth.rng_for(201, i), n_rays=n_rays, ctx=ctx, use_gpu=use_gpu, with_normals=True)
+        w.host_clouds.append((pts, cov))
+        w.host_normals.append(nrm)
         w.poses.append(traj[i])
     w.resolutions = [p.voxel_resolution * p.voxelmap_scaling_factor**l for l in range(p.voxelmap_levels)]
     w.upload()
@@ -254,8 +265,12 @@ def livox_stress(ctx, n_rays=500_000, use_gpu=False, n_targets=17) -> Workload:
     sc = synth.make_hall_scene()
     n_tgt = n_targets
     traj = synth.arc_trajectory(n_tgt + 1, step=0.5)
+    w.surface_validation = True  # odometry's factor rule (odometry_estimation_gpu.cpp:145, :162)
+    w.notes["surface_validation"] = True
     for i in range(n_tgt + 1):
-        w.host_clouds.append(make_scan(sc, "mid360", traj[i], synth.rng_for(501, i), n_rays=n_rays, ctx=ctx, use_gpu=use_gpu))
+        pts, cov, nrm = make_scan(sc, "mid360", traj[i], synth.rng_for(501, i), n_rays=n_rays, ctx=ctx, use_gpu=use_gpu, with_normals=True)
+        w.host_clouds.append((pts, cov))
+        w.host_normals.append(nrm)
         w.poses.append(traj[i])
     w.resolutions = [0.1, 0.2]
     w.upload()

@@ -152,6 +152,8 @@ GB_API gb_status gb_sweep_attach_slab(gb_sweep* sweep, void* device_slab_f32, si
 GB_API gb_status gb_sweep_set_poses(gb_sweep* sweep, const double* T_target_source /* F x 16, host */); /* async H2D */
 GB_API gb_status gb_sweep_launch(gb_sweep* sweep);                                /* async: the fused kernel */
 GB_API gb_status gb_sweep_fetch(gb_sweep* sweep, gb_linearized6* out /* F */);     /* D2H + stream sync */
+/* set_poses + launch + fetch in one call; small sweeps run it as one CUDA-graph launch (poses H2D -> kernel -> records D2H) */
+GB_API gb_status gb_sweep_linearize(gb_sweep* sweep, const double* T_target_source /* F x 16 */, gb_linearized6* out /* F */);
 GB_API gb_status gb_sweep_results_device(gb_sweep* sweep, void** device_ptr);     /* F x 122 doubles in HBM */
 /* bookkeeping for the roofline: sum of N_source, and algorithmic bytes B_sweep of SURVEY 8(d) */
 GB_API gb_status gb_sweep_stats(const gb_sweep* sweep, uint64_t* point_factors, uint64_t* algorithmic_bytes, uint32_t* num_tiles, uint32_t* grid_size);

@@ -39,6 +39,7 @@ def lib():
         L.go_gpumap_get.argtypes = [vp, vp, vp, vp, vp, vp]
         L.go_gpumap_correspondences.argtypes = [vp, i32, vp, vp, vp]
         L.go_vgicp_linearize_gpumap.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp]
+        L.go_vgicp_linearize_gpumap_sv.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp]
         L.go_vgicp_error_gpumap.restype = f64
         L.go_vgicp_error_gpumap.argtypes = [vp, i32, vp, vp, vp, vp]
         L.go_overlap_gpumap.restype = f64
@@ -157,12 +158,14 @@ class GpuMap:
         return corr
 
 
-def linearize_gpumap(m, xyz, cov6, T, with_derivs=True):
+def linearize_gpumap(m, xyz, cov6, T, with_derivs=True, normals=None):
+    """normals: (n,3|4) source normals -> surface validation on (corr == -2 marks correspondences the gate rejected)."""
     xyz, cov6 = _f32(xyz), _f32(cov6)
     out = np.zeros(122)
     corr = np.empty((xyz.shape[0],), np.int32)
     Tc = pose_colmajor(T)
-    lib().go_vgicp_linearize_gpumap(m.h, xyz.shape[0], _p(xyz), _p(cov6), _p(Tc), int(with_derivs), _p(out), _p(corr))
+    nr = _f32(np.asarray(normals)[:, :3]) if normals is not None else None
+    lib().go_vgicp_linearize_gpumap_sv(m.h, xyz.shape[0], _p(xyz), _p(cov6), _p(nr), _p(Tc), int(with_derivs), _p(out), _p(corr))
     return out, corr
 
 

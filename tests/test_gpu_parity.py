@@ -442,7 +442,7 @@ def _oracle_check_factors(ctx, w, fset, picks, tol=REL_TOL):
                 packed[c] = oracle.pack_cloud(w.host_clouds[c][0], util.cov_colmajor16(w.host_clouds[c][1]))
         if (f.target, f.level) not in maps:
             maps[(f.target, f.level)] = oracle.GpuMap(*packed[f.target], w.resolutions[f.level])
-        ref, _ = oracle.linearize_gpumap(maps[(f.target, f.level)], *packed[f.source], fset.deltas[k])
+        ref, _ = oracle.linearize_gpumap(maps[(f.target, f.level)], *packed[f.source], fset.deltas[k], normals=w.host_normals[f.source] if w.surface_validation else None)
         got = gpu.unpack_linearized(rec[k])
         check_linearized(got, ref, tol)
         worst = max(worst, util.rel_err(got["H_ss"], oracle.split122(ref)["H_ss"]))
@@ -595,3 +595,34 @@ def test_merge_frames_gpu_matches_oracle(ctx):
     m = gpu.GaussianVoxelMapGPU(0.5, ctx=ctx).insert(merged)
     got = gpu.IntegratedVGICPFactorGPU(np.eye(4), 1, m, merged, ctx=ctx).linearize({1: np.eye(4)})
     assert got["num_inliers"] == merged.size()
+
+
+def test_surface_validation_matches_oracle(ctx, dev, pair):
+    """set_enable_surface_validation(true) (odometry_estimation_gpu.cpp:145, :162): the orientation-consistency gate
+    3 n^T C_B n <= tr(C_B) (DESIGN ledger; the reference rule is unpinned) -- kernel and oracle take the same decisions (fp32,
+    canonical operation order), the gate rejects a real fraction of the correspondences, and it needs the source normals."""
+    res = 0.5
+    m = gpu.GaussianVoxelMapGPU(res, ctx=ctx).insert(dev["cloud"][0])
+    ref_map = oracle.GpuMap(dev["xyz"][0], dev["cov6"][0], res)
+    nrm = pair["normals"][1]
+    fac = gpu.IntegratedVGICPFactorGPU(0, 1, m, dev["cloud"][1], ctx=ctx)
+    fac.set_enable_surface_validation(True)
+    off = gpu.IntegratedVGICPFactorGPU(0, 1, m, dev["cloud"][1], ctx=ctx)
+    for T in util.test_poses(dev["T_gt"], 3, key=77):
+        got = fac.linearize({0: np.eye(4), 1: T})
+        ref, corr = oracle.linearize_gpumap(ref_map, dev["xyz"][1], dev["cov6"][1], T, normals=nrm.astype(np.float32))
+        check_linearized(got, ref)
+        base = off.linearize({0: np.eye(4), 1: T})
+        rejected = int((corr == -2).sum())
+        assert rejected > 0.02 * base["num_inliers"] and got["num_inliers"] == base["num_inliers"] - rejected
+        e = fac.error({0: np.eye(4), 1: T})
+        assert abs(e - got["error"]) <= 1e-5 * got["error"]
+    # batched, mixed with a factor that has the gate off
+    out = gpu.NonlinearFactorSetGPU(ctx).add([fac, off]).linearize({0: np.eye(4), 1: dev["T_gt"]})
+    assert out[0]["num_inliers"] < out[1]["num_inliers"]
+    # a frame without normals cannot use the gate: loud error, not a silent no-op
+    bare = gpu.PointCloudGPU.clone(pair["points"][1], pair["covs"][1], ctx=ctx)
+    f2 = gpu.IntegratedVGICPFactorGPU(0, 1, m, bare, ctx=ctx)
+    f2.set_enable_surface_validation(True)
+    with pytest.raises(Exception):
+        f2.linearize({0: np.eye(4), 1: dev["T_gt"]})
