@@ -49,6 +49,7 @@ def lib():
         L.go_cpumap_create.argtypes = [f64]
         L.go_cpumap_free.argtypes = [vp]
         L.go_cpumap_insert.argtypes = [vp, i32, vp, vp]
+        L.go_cpumap_set_lru.argtypes = [vp, i32, i32]
         L.go_cpumap_num_voxels.restype = i32
         L.go_cpumap_num_voxels.argtypes = [vp]
         L.go_cpumap_lookup.restype = i32
@@ -192,6 +193,10 @@ class CpuMap:
         if getattr(self, "h", None):
             lib().go_cpumap_free(self.h)
             self.h = None
+
+    def set_lru_horizon(self, horizon, clear_cycle=10):
+        """GaussianVoxelMapCPU::set_lru_horizon (odometry_estimation_cpu.cpp:67)."""
+        lib().go_cpumap_set_lru(self.h, int(horizon), int(clear_cycle))
 
     def insert(self, pts4, cov16):
         pts4 = _f64(pts4)

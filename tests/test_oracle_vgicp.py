@@ -194,3 +194,44 @@ def test_error_semantics(pair):
     far[:3, 3] += 1000.0
     assert oracle.overlap_gpumap([m], xyz1, [far]) == 0.0
     assert oracle.overlap_gpumap([m, m], xyz1, [far, T_gt]) == pytest.approx(ov)
+
+
+def test_cpu_voxelmap_lru_horizon():
+    """GaussianVoxelMapCPU::set_lru_horizon as OdometryEstimationCPU uses it (odometry_estimation_cpu.cpp:67, lru_thresh): voxels
+    that no insert touched for `horizon` inserts are erased at the next clear cycle; touched ones survive with their statistics."""
+    import numpy as np
+
+    from oracle import oracle
+
+    rng = np.random.default_rng(1)
+
+    def blob(cx, n=400):
+        p = np.concatenate([rng.uniform(-2, 2, (n, 3)) + [cx, 0, 0], np.ones((n, 1))], 1)
+        c = np.tile(np.diag([1.0, 1.0, 1.0, 0.0]), (n, 1, 1)).reshape(n, 16)
+        return p, c
+
+    m = oracle.CpuMap(0.5)
+    m.set_lru_horizon(6, clear_cycle=2)
+    keep_p, keep_c = blob(0.0)
+    m.insert(keep_p, keep_c)
+    n0 = m.num_voxels
+    j0, mean0, cov0 = m.lookup(keep_p[0, :3])
+    assert j0 >= 0
+    sizes = []
+    for k in range(1, 14):  # a sensor moving away: blob k is never touched again
+        p, c = blob(10.0 * k)
+        m.insert(p, c)
+        if k % 3 == 0:
+            m.insert(keep_p[:50], keep_c[:50])  # ... while the first region keeps being observed
+        sizes.append(m.num_voxels)
+    assert max(sizes) < n0 * 9  # without eviction it would hold all 14 blobs
+    j1, mean1, _ = m.lookup(keep_p[0, :3])
+    assert j1 >= 0  # the re-observed region survived
+    assert m.lookup(np.array([10.0, 0.0, 0.0]))[0] < 0 or m.lookup(blob(10.0)[0][0, :3])[0] < 0  # the oldest blob is gone
+    # eviction off (default): nothing disappears
+    m2 = oracle.CpuMap(0.5)
+    first = blob(0.0)
+    m2.insert(*first)
+    for k in range(1, 30):
+        m2.insert(*blob(10.0 * k))
+    assert m2.lookup(first[0][0, :3])[0] >= 0
