@@ -545,7 +545,7 @@ def test_gb_preprocess_matches_oracle_pipeline(ctx, mode):
     # and the frame is usable as a VGICP source right away
     m = gpu.GaussianVoxelMapGPU(0.5, ctx=ctx).insert(cloud)
     got = gpu.IntegratedVGICPFactorGPU(np.eye(4), 1, m, cloud, ctx=ctx).linearize({1: np.eye(4)})
-    assert got["num_inliers"] == fr.size()
+    assert fr.size() * 0.995 <= got["num_inliers"] <= fr.size()  # (the table may drop <= target_points_drop_rate of the points)
     # the PreprocessedFrame-only entry (CloudPreprocessor mirror) agrees
     fr2 = preprocess.CloudPreprocessor(par, ctx=ctx, seed=5).preprocess(10.0, T, P)
     assert np.array_equal(fr2.points, fr.points) and np.array_equal(fr2.neighbors, fr.neighbors)
@@ -594,7 +594,7 @@ def test_merge_frames_gpu_matches_oracle(ctx):
     # the merged submap is a valid VGICP target / source
     m = gpu.GaussianVoxelMapGPU(0.5, ctx=ctx).insert(merged)
     got = gpu.IntegratedVGICPFactorGPU(np.eye(4), 1, m, merged, ctx=ctx).linearize({1: np.eye(4)})
-    assert got["num_inliers"] == merged.size()
+    assert merged.size() * 0.995 <= got["num_inliers"] <= merged.size()  # (the table may drop <= target_points_drop_rate of the points)
 
 
 def test_surface_validation_matches_oracle(ctx, dev, pair):
@@ -614,9 +614,14 @@ def test_surface_validation_matches_oracle(ctx, dev, pair):
         check_linearized(got, ref)
         base = off.linearize({0: np.eye(4), 1: T})
         rejected = int((corr == -2).sum())
-        assert rejected > 0.02 * base["num_inliers"] and got["num_inliers"] == base["num_inliers"] - rejected
+        assert rejected > 0 and got["num_inliers"] == base["num_inliers"] - rejected
         e = fac.error({0: np.eye(4), 1: T})
         assert abs(e - got["error"]) <= 1e-5 * got["error"]
+    # a pose that turns the source by 60 degrees about x: normals no longer agree with the voxels they fall into
+    Tbad = dev["T_gt"] @ synth.pose(0, 0, 0, 0.0, 0.0, np.pi / 3)
+    got = fac.linearize({0: np.eye(4), 1: Tbad})
+    ref, corr = oracle.linearize_gpumap(ref_map, dev["xyz"][1], dev["cov6"][1], Tbad, normals=nrm.astype(np.float32))
+    assert got["num_inliers"] == ref[121] and (corr == -2).sum() > 0.05 * (corr != -1).sum() > 0
     # batched, mixed with a factor that has the gate off
     out = gpu.NonlinearFactorSetGPU(ctx).add([fac, off]).linearize({0: np.eye(4), 1: dev["T_gt"]})
     assert out[0]["num_inliers"] < out[1]["num_inliers"]
