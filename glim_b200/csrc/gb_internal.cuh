@@ -195,6 +195,11 @@ struct gb_ctx {
 };
 #define GB_LOCK(ctx) std::lock_guard<std::recursive_mutex> gb_lock__((ctx)->mu)
 
+// Device blocks of clouds / voxel maps come from a process-wide pool (a frame costs one cloud + two maps = five allocations;
+// cudaMalloc / cudaFree are 50-200 us each and cudaFree synchronises the device).  gb_dev_free waits for the streams of
+// every live context of the device (what the implicit synchronisation of cudaFree used to guarantee) and keeps the block.
+cudaError_t gb_dev_malloc(int device, size_t bytes, void** out);
+void gb_dev_free(int device, void* p);
 gb_status gb_ctx_scratch(gb_ctx* ctx, size_t bytes, void** out);  // device scratch, valid until the next call
 gb_status gb_ctx_pinned(gb_ctx* ctx, size_t bytes, void** out);   // pinned host staging, same lifetime rule
 

@@ -1077,7 +1077,7 @@ gb_status gb_preprocess_impl(gb_ctx* ctx, size_t n_, const double* xyzw, const d
       const size_t ctotal = 3 * c0 + c2;
       const size_t bperm = align_up(sizeof(int) * (size_t)M, 256);
       cloud_out->n = (size_t)M;
-      GB_CUDA(cudaMalloc(&cloud_out->base, ctotal + 2 * bperm));
+      GB_CUDA(gb_dev_malloc(ctx->device, ctotal + 2 * bperm, &cloud_out->base));
       cloud_out->bytes = ctotal + 2 * bperm;
       char* d = (char*)cloud_out->base;
       cloud_out->p0 = (float4*)d; cloud_out->p1 = (float4*)(d + c0); cloud_out->p2 = (float*)(d + 2 * c0); cloud_out->normals = (float4*)(d + 2 * c0 + c2);
@@ -1296,7 +1296,7 @@ gb_status gb_merge_frames_impl(gb_ctx* ctx, int K, const gb_cloud* const* frames
     const size_t ctotal = 2 * c0 + c2;
     const size_t bperm = align_up(sizeof(int) * (size_t)M, 256);
     cloud_out->n = (size_t)M;
-    GB_CUDA(cudaMalloc(&cloud_out->base, ctotal + 2 * bperm));
+    GB_CUDA(gb_dev_malloc(ctx->device, ctotal + 2 * bperm, &cloud_out->base));
     cloud_out->bytes = ctotal + 2 * bperm;
     char* d = (char*)cloud_out->base;
     cloud_out->p0 = (float4*)d; cloud_out->p1 = (float4*)(d + c0); cloud_out->p2 = (float*)(d + 2 * c0); cloud_out->normals = nullptr;

@@ -181,7 +181,7 @@ gb_status gb_voxelmap_build_impl(gb_ctx* ctx, const gb_cloud* cloud, float resol
     GB_CUDA(cudaStreamSynchronize(st));
     ctx->launches += 4;
     if (V > 0) {
-      GB_CUDA(cudaMalloc(&m->base, sizeof(float4) * 3 * (size_t)V));
+      GB_CUDA(gb_dev_malloc(ctx->device, sizeof(float4) * 3 * (size_t)V, &m->base));
       m->voxels = (float4*)m->base;
       k_voxel_starts<<<gb, tb, 0, st>>>(n, d_keys_s, d_flags, d_pos, d_starts);
       k_voxel_reduce<<<(V + 127) / 128, 128, 0, st>>>(V, d_starts, d_keys_s, d_idx_s, cloud->p0, cloud->p1, cloud->p2, cloud->inv_perm, m->voxels, d_vcoord);
@@ -198,7 +198,7 @@ gb_status gb_voxelmap_build_impl(gb_ctx* ctx, const gb_cloud* cloud, float resol
                                                              // MISS (65 % of them in global mapping) walk until the first empty slot
                                                              // (profiles/tune_tablemult_r01.txt); same rule as the oracle
   for (;;) {
-    GB_CUDA(cudaMalloc((void**)&m->buckets, sizeof(int4) * (size_t)nb));
+    GB_CUDA(gb_dev_malloc(ctx->device, sizeof(int4) * (size_t)nb, (void**)&m->buckets));
     k_table_clear<<<(nb + 255) / 256, 256, 0, st>>>(nb, m->buckets);
     ctx->launches++;
     int dropped = 0;
@@ -217,7 +217,7 @@ gb_status gb_voxelmap_build_impl(gb_ctx* ctx, const gb_cloud* cloud, float resol
     m->num_buckets = nb;
     m->num_dropped_points = dropped;
     if ((double)dropped <= drop_rate * (double)n || nb >= (1 << 28)) break;
-    GB_CUDA(cudaFree(m->buckets));
+    gb_dev_free(ctx->device, m->buckets);
     m->buckets = nullptr;
     nb *= 2;
   }

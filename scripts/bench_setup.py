@@ -41,6 +41,11 @@ def main():
         r["gpu_voxelgrid_ms"] = med(lambda: preprocess.voxelgrid_sampling(pts, 0.1, times=tms, ctx=ctx), 5)
         c16 = np.ascontiguousarray(np.swapaxes(cov, 1, 2)).reshape(n, 16)
         holder = {}
+        # the fused device-resident frame pipeline (gb_preprocess): voxel grid 0.1 m -> gates -> time order -> k-NN -> covariances -> device cloud
+        fp = preprocess.FramePreprocessorGPU(preprocess.CloudPreprocessorParams(distance_near_thresh=0.5, distance_far_thresh=100.0, downsample_resolution=0.1, k_correspondences=10), ctx)
+        r["gpu_preprocess_fused_device_cloud_ms"] = med(lambda: fp.preprocess(0.0, tms, pts, host_outputs=False), 7)
+        r["gpu_preprocess_fused_with_host_products_ms"] = med(lambda: fp.preprocess(0.0, tms, pts, host_outputs=True), 5)
+        r["frame_points_after_preprocess"] = int(fp.preprocess(0.0, tms, pts, host_outputs=False)[3].size())
 
         def up():
             holder["c"] = gpu.PointCloudGPU.clone(pts, cov, ctx=ctx)
