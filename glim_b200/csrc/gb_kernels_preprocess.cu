@@ -1085,18 +1085,32 @@ gb_status gb_preprocess_impl(gb_ctx* ctx, size_t n_, const double* xyzw, const d
       GB_CHECK(gb_cloud_reorder_impl(ctx, cloud_out, staged, c0, c0, c2, c0));
     }
   }
-  // ---- host products ----
+  // ---- host products: D2H into the context's pinned staging (full PCIe rate), then one memcpy each into the caller's arrays ----
   if (M > 0) {
-    if (out->xyzw) GB_CUDA(cudaMemcpyAsync(out->xyzw, d_fr, sizeof(double4) * (size_t)M, cudaMemcpyDeviceToHost, st));
-    if (out->times) GB_CUDA(cudaMemcpyAsync(out->times, d_frt, sizeof(double) * (size_t)M, cudaMemcpyDeviceToHost, st));
-    if (out->intensities && intensities) GB_CUDA(cudaMemcpyAsync(out->intensities, d_fri, sizeof(double) * (size_t)M, cudaMemcpyDeviceToHost, st));
-    if (out->neighbors) GB_CUDA(cudaMemcpyAsync(out->neighbors, d_nb, sizeof(int) * (size_t)M * k, cudaMemcpyDeviceToHost, st));
-    if (P->estimate_covariances && out->normals4) GB_CUDA(cudaMemcpyAsync(out->normals4, d_nrm, sizeof(double4) * (size_t)M, cudaMemcpyDeviceToHost, st));
-    if (P->estimate_covariances && out->cov4x4) GB_CUDA(cudaMemcpyAsync(out->cov4x4, d_cov, sizeof(double) * 16 * (size_t)M, cudaMemcpyDeviceToHost, st));
-    double last_t = 0.0;
-    GB_CUDA(cudaMemcpyAsync(&last_t, d_frt + (M - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+    const size_t m = (size_t)M;
+    const bool cov_out = P->estimate_covariances != 0;
+    struct Part { void* dst; const void* src; size_t bytes; };
+    Part parts[6] = {{out->xyzw, d_fr, sizeof(double4) * m}, {out->times, d_frt, sizeof(double) * m}, {(out->intensities && intensities) ? out->intensities : nullptr, d_fri, sizeof(double) * m},
+                     {out->neighbors, d_nb, sizeof(int) * m * (size_t)k}, {(cov_out ? out->normals4 : nullptr), d_nrm, sizeof(double4) * m}, {(cov_out ? out->cov4x4 : nullptr), d_cov, sizeof(double) * 16 * m}};
+    size_t total_h = 64;
+    for (const Part& q : parts) if (q.dst) total_h += align_up(q.bytes, 64);
+    char* h = nullptr;
+    GB_CHECK(gb_ctx_pinned(ctx, total_h, (void**)&h));
+    size_t off = 64;
+    GB_CUDA(cudaMemcpyAsync(h, d_frt + (M - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+    for (const Part& q : parts) {
+      if (!q.dst) continue;
+      GB_CUDA(cudaMemcpyAsync(h + off, q.src, q.bytes, cudaMemcpyDeviceToHost, st));
+      off += align_up(q.bytes, 64);
+    }
     GB_CUDA(cudaStreamSynchronize(st));
-    out->last_time = last_t;
+    memcpy(&out->last_time, h, sizeof(double));
+    off = 64;
+    for (const Part& q : parts) {
+      if (!q.dst) continue;
+      memcpy(q.dst, h + off, q.bytes);
+      off += align_up(q.bytes, 64);
+    }
   } else {
     out->last_time = 0.0;
   }
