@@ -84,7 +84,7 @@ struct FactorDesc {
   int pair;
   int flags;
   int num_tiles;
-  int first_tile;
+  int chunk;       // contiguous items: points per item of THIS factor (the last factors of a sweep get smaller items: tail tapering)
 };
 static_assert(sizeof(FactorDesc) == 80, "FactorDesc size");
 

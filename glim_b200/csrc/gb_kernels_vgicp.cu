@@ -463,7 +463,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep4(
   auto prefetch_item = [&](int it_idx, int b) {
     const int2 it = __ldg(&items[it_idx]);
     const int n = cached ? cache->desc[it.x].n : descs[it.x].n;
-    const int cnt = min(min(chunk, n - it.y), T);
+    const int fchunk = cached ? cache->desc[it.x].chunk : descs[it.x].chunk;
+    const int cnt = min(min(fchunk, n - it.y), T);
+    (void)chunk;
     if (cnt > 0) issue_factor_stage(it.x, b, it.y, cnt);
   };
   // lane 0 (after a __syncwarp): publish the ticket of the previous item's factor; is that factor complete now?
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep4(
     if (cached) P = cache->pose[f]; else P = pose_from_colmajor(poses + (size_t)f * 16);
     PoseF Pe = P;
     if (MODE == GB_MODE_ERROR) { if (cached) Pe = cache->pose_eval[f]; else Pe = pose_from_colmajor(poses_eval + (size_t)f * 16); }
-    const int item_end = min(it.y + chunk, D.n);
+    const int item_end = min(it.y + D.chunk, D.n);
     const int nstages = (max(0, item_end - it.y) + T - 1) / T;  // 0: factor without points (its epilogue still runs)
 
     float acc[32];
@@ -681,7 +683,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep3(
     const PoseF P = pose_from_colmajor(poses + (size_t)f * 16);
     PoseF Pe = P;
     if (MODE == GB_MODE_ERROR) Pe = pose_from_colmajor(poses_eval + (size_t)f * 16);
-    const int item_end = min(it.y + chunk, D.n);
+    const int item_end = min(it.y + D.chunk, D.n);  // per-factor item size (the tail of a sweep is tapered)
+    (void)chunk;
 
     float acc[32];
 #pragma unroll
@@ -834,7 +837,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep5(
     if (MODE == GB_MODE_ERROR) { if (cached) Pe = cache->pose_eval[f]; else Pe = pose_from_colmajor(poses_eval + (size_t)f * 16); }
 
     // the item's points: contiguous [it.y, it.y + chunk) or the rows it.y, it.y + J, ... (32 points each) of the cloud
-    const int limit = strided ? D.n : min(it.y + chunk, D.n);
+    const int limit = strided ? D.n : min(it.y + D.chunk, D.n);
+    (void)chunk;
     const int row_stride = strided ? D.num_tiles * 32 : 32;
     const int first = strided ? it.y * 32 : it.y;
     int ngroups = 0;

@@ -14,6 +14,8 @@ import bench  # noqa: E402
 
 CONFIGS = [
     ("v3", {"GB_KERNEL": "3"}),
+    ("auto", {}),
+    ("auto notaper", {"GB_TAPER": "0"}),
     ("v5", {"GB_KERNEL": "5"}),
     ("v5 pipe1", {"GB_KERNEL": "5", "GB_PIPE": "1"}),
     ("v5 pipe2", {"GB_KERNEL": "5", "GB_PIPE": "2"}),
@@ -29,7 +31,7 @@ CONFIGS = [
     ("v4 T64 ipw4", {"GB_KERNEL": "4", "GB_STAGE": "64", "GB_ITEMS_PER_WARP": "4"}),
     ("v4 T64 ipw2", {"GB_KERNEL": "4", "GB_STAGE": "64", "GB_ITEMS_PER_WARP": "2"}),
 ]
-KEYS = ["GB_KERNEL", "GB_STAGE", "GB_ITEMS_PER_WARP", "GB_TILE", "GB_STRIDED", "GB_MIN_ROWS", "GB_PIPE"]
+KEYS = ["GB_KERNEL", "GB_STAGE", "GB_ITEMS_PER_WARP", "GB_TILE", "GB_STRIDED", "GB_MIN_ROWS", "GB_PIPE", "GB_TAPER"]
 
 
 def main():
