@@ -667,6 +667,7 @@ extern "C" gb_status gb_sweep_create(gb_ctx* ctx, size_t F, gb_factor* const* fa
     while (nb_ref < (uint64_t)fa->target->num_voxels) nb_ref *= 2;
     s->algorithmic_bytes += (uint64_t)D.n * (48 + (sv ? 12 : 0)) + (uint64_t)fa->target->num_voxels * 48 + nb_ref * 16 + 64 + 488;  // +12 B / point: the normals, when they are read
   }
+  s->any_sv = any_sv;
   if (any_sv && s->kernel_version == 4) s->kernel_version = s->strided ? 5 : 3;  // the staged experiment does not carry normals
   build_items(s, descs.data(), tiles);
   s->num_tiles = (int)tiles.size();

@@ -112,6 +112,10 @@ __device__ __forceinline__ void accumulate_hit(float (&acc)[32], const PoseF& Pe
   float mxx, mxy, mxz, myy, myz, mzz;
   if (!fused_mahalanobis(Pe, a0.w, a1.x, a1.y, a1.z, a1.w, a2, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, mxx, mxy, mxz, myy, myz, mzz)) return;
   const float rx = v0.x - qx, ry = v0.y - qy, rz = v0.z - qz;
+  // a NaN source point converts to voxel coordinate 0 and may "hit" voxel (0, ., .): it is rejected here, on the hit path only
+  // (the oracle never finds a voxel for it) -- three instructions per HIT instead of per point
+  const float fin = (rx + ry) + rz;
+  if (!(fin == fin)) return;
   const float wx = mxx * rx + mxy * ry + mxz * rz;
   const float wy = mxy * rx + myy * ry + myz * rz;
   const float wz = mxz * rx + myz * ry + mzz * rz;
@@ -530,9 +534,6 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep4(
             float qx, qy, qz;
             transform(P, a0.x, a0.y, a0.z, qx, qy, qz);
             cx[u] = gb_coord(qx, D.inv_res); cy[u] = gb_coord(qy, D.inv_res); cz[u] = gb_coord(qz, D.inv_res);
-            // a NaN coordinate converts to 0 and would probe voxel (0, ., .): force a coordinate no voxel can have (|c| < 2^20)
-            const float sum = (qx + qy) + qz;
-            if (!(sum == sum)) cx[u] = 0x7fffffff;
             h[u] = gb_hash(cx[u], cy[u], cz[u]);
             b[u] = __ldg(&D.buckets[h[u] & D.mask]);
             b1[u] = __ldg(&D.buckets[(h[u] + 1u) & D.mask]);
@@ -658,7 +659,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep4(
 constexpr int kSubMax = 512;   // queue capacity per warp (points per round)
 constexpr int kLookupUnroll = 4;
 
-template <int MODE, bool PEER>
+template <int MODE, bool PEER, bool SV>
 __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep3(
   const FactorDesc* __restrict__ descs, const double* __restrict__ poses, const double* __restrict__ poses_eval,
   const int2* __restrict__ items, int num_items, int chunk,
@@ -704,8 +705,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep3(
           float qx, qy, qz;
           transform(P, a0.x, a0.y, a0.z, qx, qy, qz);
           cx[u] = gb_coord(qx, D.inv_res); cy[u] = gb_coord(qy, D.inv_res); cz[u] = gb_coord(qz, D.inv_res);
-          const float sum = (qx + qy) + qz;
-          if (!(sum == sum)) cx[u] = 0x7fffffff;  // NaN point: a coordinate no voxel has
           h[u] = gb_hash(cx[u], cy[u], cz[u]);
           b[u] = __ldg(&D.buckets[h[u] & D.mask]);
           b1[u] = __ldg(&D.buckets[(h[u] + 1u) & D.mask]);
@@ -731,7 +730,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep3(
         const float4 v0 = __ldg(&D.voxels[3 * (size_t)e.y + 0]);
         const float4 v1 = __ldg(&D.voxels[3 * (size_t)e.y + 1]);
         const float4 v2 = __ldg(&D.voxels[3 * (size_t)e.y + 2]);
-        if (D.normals == nullptr || surface_ok(P, __ldg(&D.normals[i]), v0.w, v1.x, v1.y, v1.z, v1.w, v2.x)) accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
+        // surface validation is a compile-time variant here (GLIM enables it for odometry factors only, which run sweep5)
+        if (!SV || D.normals == nullptr || surface_ok(P, __ldg(&D.normals[i]), v0.w, v1.x, v1.y, v1.z, v1.w, v2.x)) accumulate_hit<MODE>(acc, Pe, a0, a1, a2, v0, v1, v2);
       }
       __syncwarp();  // the queue is overwritten by the next round
     }
@@ -872,8 +872,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep5(
           float qx, qy, qz;
           transform(P, ax[u], ay[u], az[u], qx, qy, qz);
           cx[u] = gb_coord(qx, D.inv_res); cy[u] = gb_coord(qy, D.inv_res); cz[u] = gb_coord(qz, D.inv_res);
-          const float sum = (qx + qy) + qz;
-          if (!(sum == sum)) cx[u] = 0x7fffffff;  // NaN point: a coordinate no voxel has
           h[u] = gb_hash(cx[u], cy[u], cz[u]);
           b[u] = __ldg(&D.buckets[h[u] & D.mask]);
           b1[u] = __ldg(&D.buckets[(h[u] + 1u) & D.mask]);
@@ -1055,9 +1053,9 @@ static cudaError_t launch5(gb_sweep* s, const double* poses_eval, float* slab, c
   return cudaGetLastError();
 }
 
-template <int MODE, bool PEER>
+template <int MODE, bool PEER, bool SV>
 static cudaError_t launch3(gb_sweep* s, const double* poses_eval, float* slab, const PeerPush* pp) {
-  k_vgicp_sweep3<MODE, PEER><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
+  k_vgicp_sweep3<MODE, PEER, SV><<<s->grid, kThreads, 0, s->ctx->stream>>>(s->d_descs, s->d_poses, poses_eval, s->d_tiles, s->num_tiles, s->tile_size, s->d_tile_ctr, s->ctr_base, s->d_accum, s->acc_slots, s->d_done, s->d_out, slab, pp);
   return cudaGetLastError();
 }
 
@@ -1090,8 +1088,13 @@ gb_status gb_launch_sweep(gb_sweep* s, int mode) {
   const double* pe = mode == GB_MODE_ERROR ? s->d_poses_eval : nullptr;
   cudaError_t e;
   if (s->kernel_version == 3) {
-    if (mode == GB_MODE_LINEARIZE) e = peer ? launch3<GB_MODE_LINEARIZE, true>(s, pe, slab, pp) : launch3<GB_MODE_LINEARIZE, false>(s, pe, slab, pp);
-    else e = launch3<GB_MODE_ERROR, false>(s, pe, slab, pp);
+    if (s->any_sv) {
+      if (mode == GB_MODE_LINEARIZE) e = peer ? launch3<GB_MODE_LINEARIZE, true, true>(s, pe, slab, pp) : launch3<GB_MODE_LINEARIZE, false, true>(s, pe, slab, pp);
+      else e = launch3<GB_MODE_ERROR, false, true>(s, pe, slab, pp);
+    } else {
+      if (mode == GB_MODE_LINEARIZE) e = peer ? launch3<GB_MODE_LINEARIZE, true, false>(s, pe, slab, pp) : launch3<GB_MODE_LINEARIZE, false, false>(s, pe, slab, pp);
+      else e = launch3<GB_MODE_ERROR, false, false>(s, pe, slab, pp);
+    }
   } else if (s->kernel_version == 5) {
     if (mode == GB_MODE_ERROR) e = launch5<GB_MODE_ERROR, false, 0>(s, pe, slab, pp);
     else if (peer) e = launch5<GB_MODE_LINEARIZE, true, 0>(s, pe, slab, pp);
