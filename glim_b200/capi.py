@@ -81,6 +81,7 @@ def lib():
     L.gb_cloud_download.argtypes = [vp, vp, vp]
     L.gb_cloud_destroy.argtypes = [vp]
     L.gb_cloud_device_ptrs.argtypes = [vp, vp, vp, vp, vp]
+    L.gb_sweep_linearize.argtypes = [vp, vp, vp]
     L.gb_preprocess_default_params.argtypes = [vp]
     L.gb_preprocess.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.gb_merge_frames.argtypes = [vp, sz, vp, vp, f64, i32, u64, vp, vp, vp, vp]

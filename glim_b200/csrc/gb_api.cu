@@ -853,7 +853,8 @@ static gb_status sweep_linearize(gb_sweep* s, const double* T, gb_linearized6* o
     }
     s->graph_state = 1;
   }
-  memcpy(s->h_pose_slot[0], T, pose_bytes);  // the previous graph launch was synchronised below: the slot is free
+  GB_CUDA(cudaEventSynchronize(s->pose_ev[0]));  // an earlier gb_sweep_set_poses may still be reading slot 0
+  memcpy(s->h_pose_slot[0], T, pose_bytes);  // (the previous graph launch was synchronised below)
   GB_CUDA(cudaGraphLaunch(s->graph_exec, st));
   ctx->launches++;
   GB_CUDA(cudaStreamSynchronize(st));

@@ -320,6 +320,12 @@ class Sweep:
         check(lib().gb_sweep_linearize(self.h, ptr(self._poses), ptr(out)))
         return out
 
+    def linearize_raw(self, poses16: np.ndarray, out: np.ndarray) -> np.ndarray:
+        """The same call with caller-owned buffers (poses16: (F,16) float64 column-major, out: (F,) LIN_DTYPE): no Python-side
+        array work around the C entry point."""
+        check(lib().gb_sweep_linearize(self.h, poses16.ctypes.data, out.ctypes.data))
+        return out
+
     def results_device_ptr(self) -> int:
         p = C.c_void_p()
         check(lib().gb_sweep_results_device(self.h, C.byref(p)))
