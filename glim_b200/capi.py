@@ -41,7 +41,7 @@ class PreprocessParams(C.Structure):
     """gb_preprocess_params (include/glim_b200.h)."""
     _fields_ = [("distance_near_thresh", C.c_double), ("distance_far_thresh", C.c_double), ("use_random_grid_downsampling", C.c_int), ("downsample_resolution", C.c_double),
                 ("downsample_target", C.c_int), ("downsample_rate", C.c_double), ("seed", C.c_uint64), ("global_shutter", C.c_int), ("crop_bbox_frame", C.c_int),
-                ("crop_bbox_min", C.c_double * 3), ("crop_bbox_max", C.c_double * 3), ("T_imu_lidar", C.c_double * 16), ("enable_outlier_removal", C.c_int),
+                ("crop_bbox_min", C.c_double * 3), ("crop_bbox_max", C.c_double * 3), ("T_imu_lidar", C.c_double * 16), ("enable_outlier_removal", C.c_int), ("outlier_removal_k", C.c_int), ("outlier_std_mul_factor", C.c_double),
                 ("k_correspondences", C.c_int), ("estimate_covariances", C.c_int), ("k_neighbors_cov", C.c_int), ("knn_cell_size", C.c_double)]
 
 

@@ -1207,6 +1207,8 @@ extern "C" gb_status gb_preprocess_default_params(gb_preprocess_params* p) {
   p->downsample_target = 10000;       // :24
   p->downsample_rate = 0.1;           // :25
   p->seed = 0;
+  p->outlier_removal_k = 10;          // :27
+  p->outlier_std_mul_factor = 1.0;    // :28
   p->k_correspondences = 10;          // :33
   p->estimate_covariances = 1;
   for (int i = 0; i < 4; i++) p->T_imu_lidar[i * 5] = 1.0;
@@ -1218,7 +1220,7 @@ extern "C" gb_status gb_preprocess(gb_ctx* ctx, size_t n, const double* xyzw, co
   GB_REQUIRE(n < (size_t)1 << 30, "too many points");
   GB_REQUIRE(P->k_correspondences > 0, "k_correspondences must be positive");
   GB_REQUIRE(P->k_neighbors_cov >= 0 && P->k_neighbors_cov <= P->k_correspondences, "k_neighbors_cov must be in [0, k_correspondences]");
-  GB_REQUIRE(!P->enable_outlier_removal, "statistical outlier removal is not implemented (its rule lives in the un-vendored gtsam_points)");
+  GB_REQUIRE(!P->enable_outlier_removal || (P->outlier_removal_k > 0 && P->outlier_removal_k <= 32), "outlier_removal_k must be in [1, 32]");
   GB_REQUIRE(P->crop_bbox_frame >= 0 && P->crop_bbox_frame <= 2, "crop_bbox_frame must be 0 (off), 1 (lidar) or 2 (imu)");
   if (n == 0) return GB_OK;
   GB_REQUIRE(xyzw, "null points");

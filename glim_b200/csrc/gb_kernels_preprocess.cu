@@ -905,6 +905,48 @@ __global__ void __launch_bounds__(128) k_covariances_planes(int n_upper, const i
   s3[i] = make_float4((float)nx, (float)ny, (float)nz, 0.f);
 }
 
+// ---- statistical outlier removal (cloud_preprocessor.cpp:165-167: gtsam_points::remove_outliers(frame, k, std_mul, threads)) [EXT]:
+// d_i = mean distance of point i to its k nearest neighbours (the query itself included, as the k-NN returns it);
+// keep i iff d_i < mean(d) + std_mul * sqrt(mean(d^2) - mean(d)^2)   (population variance over the frame) ----
+__global__ void k_sor_dists(int n_upper, const int* __restrict__ count, const double4* __restrict__ pts, const int* __restrict__ nb, int k, double* __restrict__ dist, double* __restrict__ dist2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_upper) return;
+  double d = 0.0;
+  if (i < *count) {
+    const double4 p = pts[i];
+    double s = 0.0;
+    for (int j = 0; j < k; j++) {
+      const double4 q = pts[nb[(size_t)i * k + j]];
+      const double ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+      s += sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez)));
+    }
+    d = s / k;
+  }
+  dist[i] = d;
+  dist2[i] = __dmul_rn(d, d);
+}
+__global__ void k_sor_flags(int n_upper, const int* __restrict__ count, const double* __restrict__ dist, const double* __restrict__ sums /* [0] = sum d, [1] = sum d^2 */, double std_mul, int* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_upper) return;
+  const int m = *count;
+  const double mean = sums[0] / m;
+  const double var = sums[1] / m - mean * mean;
+  const double thresh = mean + std_mul * sqrt(var > 0.0 ? var : 0.0);
+  keep[i] = (i < m && dist[i] < thresh) ? 1 : 0;
+}
+__global__ void k_sor_compact(int n_upper, const int* __restrict__ keep, const int* __restrict__ pos, const double4* __restrict__ pts, const double* __restrict__ times, const double* __restrict__ intens,
+                              double4* __restrict__ o_pts, double* __restrict__ o_times, double* __restrict__ o_intens, int* __restrict__ count_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_upper) return;
+  if (keep[i]) {
+    const int o = pos[i] - 1;
+    o_pts[o] = pts[i];
+    o_times[o] = times[i];
+    if (intens) o_intens[o] = intens[i];
+  }
+  if (i == n_upper - 1) *count_out = pos[i];
+}
+
 template <int K>
 static void launch_knn_pyramid(int n, const double4* pts_s, const unsigned long long* keys_s, const int* idx_s, const MlCell* tables, unsigned ts, double inv_h0, double h0, int* nb, cudaStream_t st) {
   k_knn_pyramid<K><<<(n + 127) / 128, 128, 0, st>>>(n, pts_s, keys_s, idx_s, tables, ts, inv_h0, h0, nb);
@@ -958,16 +1000,19 @@ gb_status gb_preprocess_impl(gb_ctx* ctx, size_t n_, const double* xyzw, const d
   size_t cub_sort = 0, cub_scan = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_sort, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, n, 0, 64, st);
   cub::DeviceScan::InclusiveSum(nullptr, cub_scan, (int*)nullptr, (int*)nullptr, n, st);
-  size_t cub_keys = 0;
+  size_t cub_keys = 0, cub_red = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, cub_keys, (unsigned long long*)nullptr, (unsigned long long*)nullptr, n, 0, 64, st);
-  const size_t cub_b = align_up(std::max(std::max(cub_sort, cub_scan), cub_keys), 256);
+  cub::DeviceReduce::Sum(nullptr, cub_red, (double*)nullptr, (double*)nullptr, n, st);
+  const size_t cub_b = align_up(std::max(std::max(std::max(cub_sort, cub_scan), cub_keys), cub_red), 256);
   unsigned ts = 1024;
   while (ts < 2u * (unsigned)n) ts <<= 1;
   const size_t N = (size_t)n;
   const size_t planes = 2 * align_up(16 * N, 256) + align_up(4 * N, 256) + align_up(16 * N, 256);
   const size_t total = cub_b + 256 /*counters*/ + 3 * align_up(32 * N, 256) /*raw, ds, frame pts*/ + 6 * align_up(8 * N, 256) /*times, intens x3*/ + 4 * align_up(8 * N, 256) /*keys x2 (+2 knn)*/
                        + 8 * align_up(4 * (N + 1), 256) /*idx, flags, pos, starts, keep ...*/ + align_up(4 * N * (size_t)k, 256) + align_up(32 * N, 256) /*normals*/ + align_up(128 * N, 256) /*covs*/
-                       + align_up(32 * N, 256) /*knn pts_s*/ + align_up(sizeof(MlCell) * (size_t)kMlLevels * ts, 256) + gb_cloud_reorder_scratch_bytes(N, planes) + 4096;
+                       + align_up(32 * N, 256) /*knn pts_s*/ + align_up(sizeof(MlCell) * (size_t)kMlLevels * ts, 256) + gb_cloud_reorder_scratch_bytes(N, planes) + 4096
+                       + (P->enable_outlier_removal ? align_up(4 * N * (size_t)std::max(1, P->outlier_removal_k), 256) + 4 * align_up(8 * N, 256) + align_up(32 * N, 256) + 256  /* SOR arrays */
+                                                          + 2 * align_up(8 * N, 256) + 2 * align_up(4 * N, 256) + align_up(32 * N, 256) + align_up(sizeof(MlCell) * (size_t)kMlLevels * ts, 256) /* second k-NN */ : 0);
   char* base = nullptr;
   GB_CHECK(gb_ctx_scratch(ctx, total, (void**)&base));
   Carver cv{base, 0};
@@ -1056,11 +1101,37 @@ gb_status gb_preprocess_impl(gb_ctx* ctx, size_t n_, const double* xyzw, const d
   }
   k_gather_frame<<<gb, tb, 0, st>>>(n, d_cnt + 2, d_idx_s, cur_pts, cur_t, cur_i, P->global_shutter, d_fr, d_frt, d_fri);
   ctx->launches += 3;
+  const double h0 = P->knn_cell_size > 0.0 ? P->knn_cell_size : 0.25;
+  const int* frame_cnt = d_cnt + 2;
+  // ---- statistical outlier removal (optional) ----
+  if (P->enable_outlier_removal) {
+    const int ko = P->outlier_removal_k;
+    int* d_nbo = cv.take<int>(N * (size_t)ko);
+    double* d_dist = cv.take<double>(N);
+    double* d_dist2 = cv.take<double>(N);
+    double* d_sums = cv.take<double>(32);
+    double4* d_fr2 = cv.take<double4>(N);
+    double* d_frt2 = cv.take<double>(N);
+    double* d_fri2 = cv.take<double>(N);
+    GB_CHECK(knn_device(ctx, n, d_cnt + 2, d_fr, ko, h0, d_nbo, cv, cub_b, d_cub));
+    k_sor_dists<<<gb, tb, 0, st>>>(n, d_cnt + 2, d_fr, d_nbo, ko, d_dist, d_dist2);
+    size_t tmp = cub_b;
+    GB_CUDA(cub::DeviceReduce::Sum(d_cub, tmp, d_dist, d_sums, n, st));
+    tmp = cub_b;
+    GB_CUDA(cub::DeviceReduce::Sum(d_cub, tmp, d_dist2, d_sums + 1, n, st));
+    k_sor_flags<<<gb, tb, 0, st>>>(n, d_cnt + 2, d_dist, d_sums, P->outlier_std_mul_factor, d_keep);
+    tmp = cub_b;
+    GB_CUDA(cub::DeviceScan::InclusiveSum(d_cub, tmp, d_keep, d_pos, n, st));
+    k_sor_compact<<<gb, tb, 0, st>>>(n, d_keep, d_pos, d_fr, d_frt, intensities ? d_fri : nullptr, d_fr2, d_frt2, d_fri2, d_cnt + 4);
+    ctx->launches += 6;
+    d_fr = d_fr2; d_frt = d_frt2; d_fri = d_fri2;
+    frame_cnt = d_cnt + 4;
+  }
   // ---- k-NN ----
-  GB_CHECK(knn_device(ctx, n, d_cnt + 2, d_fr, k, P->knn_cell_size > 0.0 ? P->knn_cell_size : 0.25, d_nb, cv, cub_b, d_cub));
+  GB_CHECK(knn_device(ctx, n, frame_cnt, d_fr, k, h0, d_nb, cv, cub_b, d_cub));
   // ---- the frame's point count (the one host synchronisation before the results) ----
   int M = 0;
-  GB_CUDA(cudaMemcpyAsync(&M, d_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaMemcpyAsync(&M, frame_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
   GB_CUDA(cudaStreamSynchronize(st));
   out->num_points = (size_t)M;
   // ---- covariances, written straight into the staged fp32 planes of the cloud (PointCloudGPU::clone on the device) ----
@@ -1070,7 +1141,7 @@ gb_status gb_preprocess_impl(gb_ctx* ctx, size_t n_, const double* xyzw, const d
     float4* s1 = (float4*)(staged + c0);
     float* s2 = (float*)(staged + 2 * c0);
     float4* s3 = (float4*)(staged + 2 * c0 + c2);
-    k_covariances_planes<<<(M + 127) / 128, 128, 0, st>>>(M, d_cnt + 2, d_fr, d_nb, k, P->k_neighbors_cov > 0 ? P->k_neighbors_cov : k, d_nrm, d_cov, s0, s1, s2, s3);
+    k_covariances_planes<<<(M + 127) / 128, 128, 0, st>>>(M, frame_cnt, d_fr, d_nb, k, P->k_neighbors_cov > 0 ? P->k_neighbors_cov : k, d_nrm, d_cov, s0, s1, s2, s3);
     GB_CUDA(cudaGetLastError());
     ctx->launches++;
     if (cloud_out) {

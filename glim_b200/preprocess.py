@@ -31,7 +31,9 @@ class CloudPreprocessorParams:
     downsample_resolution: float = 0.15      # :31
     downsample_target: int = 0               # :32
     downsample_rate: float = 0.3             # :33
-    enable_outlier_removal: bool = False     # :34  (True is rejected: the rule lives in the un-vendored gtsam_points)
+    enable_outlier_removal: bool = False     # :34
+    outlier_removal_k: int = 10              # :35
+    outlier_std_mul_factor: float = 2.0      # :36
     enable_cropbox_filter: bool = False      # :38
     crop_bbox_frame: str = "lidar"           # :39
     crop_bbox_min: tuple = (0.0, 0.0, 0.0)
@@ -43,7 +45,7 @@ class CloudPreprocessorParams:
     @staticmethod
     def from_shipped_config() -> "CloudPreprocessorParams":
         return CloudPreprocessorParams(distance_near_thresh=0.5, distance_far_thresh=100.0, use_random_grid_downsampling=True, downsample_resolution=1.0, downsample_target=10000,
-                                       downsample_rate=0.1, crop_bbox_min=(-1.0, -1.0, -1.0), crop_bbox_max=(1.0, 1.0, 1.0), k_correspondences=10)
+                                       downsample_rate=0.1, outlier_std_mul_factor=1.0, crop_bbox_min=(-1.0, -1.0, -1.0), crop_bbox_max=(1.0, 1.0, 1.0), k_correspondences=10)
 
 
 @dataclasses.dataclass
@@ -122,8 +124,6 @@ class CloudPreprocessor:
         self.seed = seed
 
     def preprocess(self, stamp: float, times, points, intensities=None) -> PreprocessedFrame:
-        if self.params.enable_outlier_removal:
-            raise NotImplementedError("statistical outlier removal (cloud_preprocessor.cpp:165-167) is not implemented: its rule lives in the un-vendored gtsam_points")
         from .capi import Preprocessed
 
         ctx = self.ctx or default_context()
@@ -173,6 +173,7 @@ class FramePreprocessorGPU:
             for r in range(4):
                 cp.T_imu_lidar[c * 4 + r] = T[r, c]
         cp.enable_outlier_removal = int(p.enable_outlier_removal)
+        cp.outlier_removal_k, cp.outlier_std_mul_factor = p.outlier_removal_k, p.outlier_std_mul_factor
         cp.k_correspondences = p.k_correspondences
         cp.estimate_covariances = 1
         cp.knn_cell_size = self.knn_cell_size

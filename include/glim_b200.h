@@ -207,8 +207,8 @@ GB_API gb_status gb_voxelgrid_sampling(gb_ctx* ctx, size_t n, const double* xyzw
  *      and PointCloudGPU::clone (odometry_estimation_gpu.cpp:96): one H2D of the raw scan, no host round trip between the
  *      stages, the fp32 planes of the resulting gb_cloud written by the covariance kernel.  Host products (the
  *      PreprocessedFrame fields, fp64 covariances / normals) are copied back only for the pointers that are not NULL.
- *      Not implemented: statistical outlier removal (:165-167; its rule lives in the un-vendored gtsam_points) -> the call
- *      fails with GB_ERR_INVALID_ARGUMENT when enable_outlier_removal is set.
+ *      Statistical outlier removal (:165-167; gtsam_points::remove_outliers [EXT]): d_i = mean distance to the k nearest
+ *      neighbours (query included); keep i iff d_i < mean(d) + std_mul * stddev(d) (population variance).
  *      Random grid: which points of a voxel survive is a draw from std::mt19937 in the reference (not reproducible); here it
  *      is the ceil(rate N / V) points with the smallest hash(seed, index) -- same count per voxel, a fixed pseudo-random pick. ---- */
 typedef struct gb_preprocess_params {
@@ -222,7 +222,9 @@ typedef struct gb_preprocess_params {
   int crop_bbox_frame;                              /* 0 = off, 1 = "lidar", 2 = "imu" */
   double crop_bbox_min[3], crop_bbox_max[3];
   double T_imu_lidar[16];                           /* column-major; used by crop_bbox_frame == 2 */
-  int enable_outlier_removal;                       /* must be 0 */
+  int enable_outlier_removal;                       /* config_preprocess.json:26 */
+  int outlier_removal_k;                            /* 10 */
+  double outlier_std_mul_factor;                    /* code default 2.0 (cloud_preprocessor.cpp:36), shipped config 1.0 */
   int k_correspondences;                            /* k of the k-NN (10) */
   int estimate_covariances;                         /* fuse CloudCovarianceEstimation + the device cloud */
   int k_neighbors_cov;                              /* neighbours used by the covariance (<= k_correspondences; 0 = all) */

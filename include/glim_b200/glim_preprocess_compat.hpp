@@ -81,7 +81,6 @@ public:
 
   /// cloud_preprocessor.cpp:77-188 in one device-resident call
   virtual PreprocessedFrame::Ptr preprocess(const RawPoints::ConstPtr& raw_points) {
-    if (params.enable_outlier_removal) throw std::runtime_error("CloudPreprocessor: statistical outlier removal is not implemented by libglim_b200");
     gb_preprocess_params cp = c_params();
     cp.estimate_covariances = 0;
     const std::size_t n = raw_points->points.size();
@@ -129,6 +128,8 @@ public:
     for (int a = 0; a < 3; a++) { cp.crop_bbox_min[a] = params.crop_bbox_min[a]; cp.crop_bbox_max[a] = params.crop_bbox_max[a]; }
     for (int e = 0; e < 16; e++) cp.T_imu_lidar[e] = params.T_imu_lidar.m[static_cast<std::size_t>(e)];
     cp.enable_outlier_removal = params.enable_outlier_removal;
+    cp.outlier_removal_k = params.outlier_removal_k;
+    cp.outlier_std_mul_factor = params.outlier_std_mul_factor;
     cp.k_correspondences = params.k_correspondences;
     cp.estimate_covariances = 1;
     return cp;
@@ -179,7 +180,6 @@ private:
 };
 
 inline gtsam_points::PointCloudGPU::Ptr CloudPreprocessor::preprocess_to_gpu_frame(const RawPoints::ConstPtr& raw_points, PreprocessedFrame::Ptr* preprocessed) {
-  if (params.enable_outlier_removal) throw std::runtime_error("CloudPreprocessor: statistical outlier removal is not implemented by libglim_b200");
   gb_preprocess_params cp = c_params();
   const std::size_t n = raw_points->points.size();
   auto fr = std::make_shared<PreprocessedFrame>();

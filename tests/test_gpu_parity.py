@@ -490,7 +490,7 @@ def test_livox_dense_factor_matches_oracle(ctx):
 
 
 # ---------------------------------------------------------------------------------------------- gb_preprocess (device-resident frame pipeline)
-def _cpu_frame(P, T, res, near, far, k, mask=None, crop=None):
+def _cpu_frame(P, T, res, near, far, k, mask=None, crop=None, sor=None):
     """oracle composition of CloudPreprocessor::preprocess_impl + CloudCovarianceEstimation::estimate"""
     if mask is None:
         pts, tms, _ = oracle.voxelgrid_sampling(P, res, times=T)
@@ -504,12 +504,24 @@ def _cpu_frame(P, T, res, near, far, k, mask=None, crop=None):
     idx = np.nonzero(keep)[0]
     idx = idx[np.argsort(tms[idx], kind="stable")]
     pts, tms = np.ascontiguousarray(pts[idx]), tms[idx]
+    if sor is not None:  # gtsam_points::remove_outliers [EXT]: mean neighbour distance vs mean + std_mul * stddev over the frame
+        ko, mul = sor
+        nbo, _ = oracle.knn_bruteforce(pts, ko)
+        d = np.zeros(len(pts))
+        for j in range(ko):
+            e = pts[:, :3] - pts[nbo[:, j], :3]
+            d = d + np.sqrt((e[:, 0] * e[:, 0] + e[:, 1] * e[:, 1]) + e[:, 2] * e[:, 2])
+        d = d / ko
+        mean = d.sum() / len(d)
+        var = (d * d).sum() / len(d) - mean * mean
+        keep = d < mean + mul * np.sqrt(max(var, 0.0))
+        pts, tms = np.ascontiguousarray(pts[keep]), tms[keep]
     nb, _ = oracle.knn_bruteforce(pts, k)
     normals, covs = oracle.covariance_estimate(pts, nb)
     return pts, tms, nb, normals, covs
 
 
-@pytest.mark.parametrize("mode", ["voxelgrid", "randomgrid", "cropbox"])
+@pytest.mark.parametrize("mode", ["voxelgrid", "randomgrid", "cropbox", "outliers"])
 def test_gb_preprocess_matches_oracle_pipeline(ctx, mode):
     """One device-resident call = the reference's whole per-frame preprocess + covariance estimation + PointCloudGPU::clone:
     frame points / times bit-exact, neighbour indices exact, covariances 1e-9, and the device cloud equals the fp32 cast of
@@ -526,6 +538,10 @@ def test_gb_preprocess_matches_oracle_pipeline(ctx, mode):
         mask = oracle.randomgrid_sampling(P, 1.0, 6000 / len(P), seed=5)
         assert 5000 < mask.sum() <= int(len(P) * (6000 / len(P)) * 1.2)
         ref = _cpu_frame(P, T, None, 1.0, 60.0, k, mask=mask)
+    elif mode == "outliers":
+        par = preprocess.CloudPreprocessorParams(distance_near_thresh=1.0, distance_far_thresh=60.0, downsample_resolution=0.2, k_correspondences=k, enable_outlier_removal=True, outlier_removal_k=8, outlier_std_mul_factor=1.0)
+        ref = _cpu_frame(P, T, 0.2, 1.0, 60.0, k, sor=(8, 1.0))
+        assert len(ref[0]) < 0.97 * len(_cpu_frame(P, T, 0.2, 1.0, 60.0, k)[0])  # the filter removes a real share of the (far, sparse) points
     elif mode == "cropbox":
         par = preprocess.CloudPreprocessorParams(distance_near_thresh=1.0, distance_far_thresh=60.0, downsample_resolution=0.2, k_correspondences=k, enable_cropbox_filter=True, crop_bbox_min=(-3.0, -2.0, -5.0), crop_bbox_max=(4.0, 2.5, 5.0))
         ref = _cpu_frame(P, T, 0.2, 1.0, 60.0, k, crop=(np.array([-3.0, -2.0, -5.0]), np.array([4.0, 2.5, 5.0])))
