@@ -16,6 +16,9 @@ CONFIGS = [
     ("v3", {"GB_KERNEL": "3"}),
     ("auto", {}),
     ("auto notaper", {"GB_TAPER": "0"}),
+    ("auto ipw10", {"GB_ITEMS_PER_WARP": "10"}),
+    ("auto ipw16", {"GB_ITEMS_PER_WARP": "16"}),
+    ("auto ipw24", {"GB_ITEMS_PER_WARP": "24"}),
     ("v5", {"GB_KERNEL": "5"}),
     ("v5 pipe1", {"GB_KERNEL": "5", "GB_PIPE": "1"}),
     ("v5 pipe2", {"GB_KERNEL": "5", "GB_PIPE": "2"}),
