@@ -507,8 +507,9 @@ static void build_items(gb_sweep* s, FactorDesc* descs, std::vector<int2>& tiles
     uint64_t total = 0;
     for (size_t f = 0; f < F; f++) total += (uint64_t)descs[f].n;
     const bool taper = env_int("GB_TAPER", 1) != 0;
-    const uint64_t tail16 = taper ? (uint64_t)(warps * s->tile_size * 0.4) : 0;  // last 0.4 item-times per warp: 1/16 items
-    const uint64_t tail4 = taper ? (uint64_t)(warps * s->tile_size * 1.5) : 0;   // last 1.5 item-times per warp: 1/4 items
+    const double ta = env_int("GB_TAPER_A", 150) * 0.01, tb = env_int("GB_TAPER_B", 40) * 0.01;
+    const uint64_t tail16 = taper ? (uint64_t)(warps * s->tile_size * tb) : 0;  // last 0.4 item-times per warp: 1/16 items
+    const uint64_t tail4 = taper ? (uint64_t)(warps * s->tile_size * ta) : 0;   // last 1.5 item-times per warp: 1/4 items
     uint64_t before = 0;
     for (size_t f = 0; f < F; f++) {
       FactorDesc& D = descs[f];

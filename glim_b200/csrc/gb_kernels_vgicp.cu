@@ -21,12 +21,14 @@
 // writes the 122-double record (and pushes the finished pair row to every rank's slab when one is attached),
 // and re-zeroes the accumulator for the next sweep.
 //
-// Two generations of the sweep kernel live here:
-//   k_vgicp_sweep4  (default)  source tiles staged into shared memory by 1-D bulk async copies (cp.async.bulk /
-//                   UBLKCP + mbarrier), double-buffered per warp; descriptor / pose cache in shared memory for small
-//                   factor sets; release-atomic tickets published lazily (no __threadfence, no L1 flush per item);
-//                   carry-over hit queue so the derivative pass always runs on full warps.
-//   k_vgicp_sweep3  (GB_KERNEL=3) the round-1 kernel: register-staged loads, fence + ticket per item.  Kept for A/B.
+// Three sweep kernels live here; gb_sweep_create picks by sweep size (GB_KERNEL = 3 / 4 / 5 forces one):
+//   k_vgicp_sweep3  large sweeps (sub mapping, global mapping): contiguous items of up to 2048 points from a global queue,
+//                   register-staged loads, lazily published release tickets, tapered items at the tail of the sweep.
+//   k_vgicp_sweep5  small sweeps (an odometry frame, a single pair -- about one item per warp): one wave of STRIDED items
+//                   sized by each factor's last inlier fraction, descriptor / pose cache in shared memory.
+//   k_vgicp_sweep4  experiment, never the default: source tiles staged into shared memory by bulk async copies
+//                   (cp.async.bulk / UBLKCP + mbarrier).  1.7-2x slower than sweep3 (profiles/r02_ab_kernels_a.txt): the
+//                   carve-out shrinks L1 and the path is latency-, not issue-bound.  Kept as the measured negative result.
 #include "gb_internal.cuh"
 
 #include <stdlib.h>
@@ -654,7 +656,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_vgicp_sweep4(
 }
 
 // =============================================================================================
-// k_vgicp_sweep3 -- the round-1 kernel (register-staged loads; fence + ticket per item).  GB_KERNEL=3.
+// k_vgicp_sweep3 -- the large-sweep kernel: register-staged loads, contiguous items drawn from a global queue (the atomic
+// for the next item is issued at the start of the current one).  An item's completion ticket is published LAZILY: an
+// atom.release issued while the next item's first loads are in flight (no __threadfence, i.e. no MEMBAR.SC + L1
+// invalidation per item), and a factor's epilogue runs after the next item's reduction.  Measured on the global-mapping
+// sweep and its 1/8 shards (profiles/r02_shard_emulate.txt): -1.6 % / -3.4 % against fence + ticket per item.
+// Tried and dropped (same file): reading the queue one item ahead in registers (+2 % time: the kernel sits at the 128-register
+// cap) and copying the next item's descriptor / pose to shared memory with cp.async during the current item (+1.6 %: the
+// three dependent L2 round trips between two items are already covered by the other 15 warps of the SM).
 // =============================================================================================
 constexpr int kSubMax = 512;   // queue capacity per warp (points per round)
 constexpr int kLookupUnroll = 4;
@@ -669,24 +678,31 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep3(
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   uint2* __restrict__ q = s_q[warp];
+  (void)chunk;
 
   // first item: static (warp id); further items (only when there are more items than warps) come from the global queue
   const int total_warps = gridDim.x * kWarps;
   const bool dynamic = num_items > total_warps;
   int item = blockIdx.x * kWarps + warp;
+  if (item >= num_items) return;
+  int2 it = __ldg(&items[item]);
+  int pend_f = -1, pend_last = 0, pend_tiles = 0;
+  auto publish = [&]() {  // lane 0, after a __syncwarp: the previous item's ticket
+    const unsigned t = ticket_release(&done[pend_f]);
+    pend_last = (t == (unsigned)pend_tiles - 1u);
+    if (pend_last) done[pend_f] = 0u;  // self-cleaning
+  };
 
-  while (item < num_items) {
+  while (true) {
     int next_item = 0x7fffffff;
     if (dynamic && lane == 0) next_item = (int)(atomicAdd(item_ctr, 1ull) - ctr_base) + total_warps;  // latency hidden behind the item
-    const int2 it = __ldg(&items[item]);
     const int f = it.x;
     const FactorDesc D = descs[f];
     const PoseF P = pose_from_colmajor(poses + (size_t)f * 16);
     PoseF Pe = P;
     if (MODE == GB_MODE_ERROR) Pe = pose_from_colmajor(poses_eval + (size_t)f * 16);
     const int item_end = min(it.y + D.chunk, D.n);  // per-factor item size (the tail of a sweep is tapered)
-    (void)chunk;
-
+    bool published = pend_f < 0;
     float acc[32];
 #pragma unroll
     for (int k = 0; k < 32; k++) acc[k] = 0.f;
@@ -708,6 +724,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep3(
           h[u] = gb_hash(cx[u], cy[u], cz[u]);
           b[u] = __ldg(&D.buckets[h[u] & D.mask]);
           b1[u] = __ldg(&D.buckets[(h[u] + 1u) & D.mask]);
+        }
+        if (!published) {  // the MEMBAR of the release overlaps with the loads above
+          published = true;
+          __syncwarp();
+          if (lane == 0) publish();
         }
 #pragma unroll
         for (int u = 0; u < kLookupUnroll; u++) {
@@ -735,6 +756,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep3(
       }
       __syncwarp();  // the queue is overwritten by the next round
     }
+    if (!published) {  // the item had no lookup group (empty factor)
+      __syncwarp();
+      if (lane == 0) publish();
+    }
 
     double* __restrict__ my_acc = accum + ((size_t)f * acc_slots + (size_t)(item & (acc_slots - 1))) * GB_ACC_STRIDE;
     if (MODE == GB_MODE_LINEARIZE) {
@@ -747,22 +772,25 @@ __global__ void __launch_bounds__(kThreads, 2) k_vgicp_sweep3(
       if (lane == 27) atomicAdd(&my_acc[27], (double)e);
       if (lane == 28) atomicAdd(&my_acc[28], (double)n);
     }
-    __threadfence();
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) {
-      const unsigned ticket = atomicAdd(&done[f], 1u);
-      last = (ticket == (unsigned)D.num_tiles - 1u);
-      if (last) done[f] = 0u;  // self-cleaning
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      __threadfence();
-      factor_epilogue(f, D, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, acc_slots, out, slab, reinterpret_cast<double*>(q));
-      if (PEER && MODE == GB_MODE_LINEARIZE) pair_push(D, out, peer, reinterpret_cast<float*>(q) + 512);
+    if (pend_f >= 0 && __shfl_sync(0xffffffffu, pend_last, 0)) {  // the PREVIOUS item completed its factor
+      fence_acquire();
+      const FactorDesc Dp = descs[pend_f];
+      factor_epilogue(pend_f, Dp, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, acc_slots, out, slab, reinterpret_cast<double*>(q));
+      if (PEER && MODE == GB_MODE_LINEARIZE) pair_push(Dp, out, peer, reinterpret_cast<float*>(q) + 512);
       __syncwarp();
     }
+    pend_f = f; pend_tiles = D.num_tiles; pend_last = 0;
     item = __shfl_sync(0xffffffffu, next_item, 0);
+    if (item >= num_items) break;
+    it = __ldg(&items[item]);
+  }
+  __syncwarp();
+  if (lane == 0) publish();
+  if (__shfl_sync(0xffffffffu, pend_last, 0)) {
+    fence_acquire();
+    const FactorDesc Dp = descs[pend_f];
+    factor_epilogue(pend_f, Dp, MODE == GB_MODE_ERROR ? poses_eval : poses, accum, acc_slots, out, slab, reinterpret_cast<double*>(q));
+    if (PEER && MODE == GB_MODE_LINEARIZE) pair_push(Dp, out, peer, reinterpret_cast<float*>(q) + 512);
   }
 }
 
@@ -1110,7 +1138,7 @@ gb_status gb_launch_sweep(gb_sweep* s, int mode) {
     else e = launch4<GB_MODE_ERROR, 128, false, 2>(s, pe, slab, pp);
   }
   if (e != cudaSuccess) { gb_set_error("sweep launch failed: %s", cudaGetErrorString(e)); return GB_ERR_CUDA; }
-  // queue bookkeeping: a sweep with more items than warps draws one ticket per processed item, plus (v4) one per warp for
+  // queue bookkeeping: a sweep with more items than warps draws one ticket per processed item, plus (v4, v5) one per warp for
   // the one-item look-ahead
   const unsigned long long warps = (unsigned long long)s->grid * kWarps;
   if ((unsigned long long)s->num_tiles > warps) s->ctr_base += (s->kernel_version == 3 ? 0ull : warps) + (unsigned long long)s->num_tiles;
