@@ -581,14 +581,15 @@ def main():
     sizes = [len(c[0]) for c in w.host_clouds]
     fused = args.collective == "fused"
 
-    def make_sweeps(inliers_by_set=None, reuse_peers=None):
+    def make_sweeps(inliers_by_set=None, reuse_peers=None, scale_by_set=None):
         """Partition every factor set over the ranks and prepare this rank's sweeps.  inliers_by_set: measured inlier counts per
         factor (from a calibration sweep) for the cost-balanced partition; None -> the overlap estimate of the gate."""
         sweeps, slabs, peers, my_pf, my_bytes, all_pf = [], [], [], 0, 0, 0
         for si, fset in enumerate(w.sets):
             if sharded:
                 f_rank, _ = multi_gpu.shard_factors(fset.factors, sizes, world, pair_cost=w.notes.get("_pair_overlap"),
-                                                    factor_inliers=None if inliers_by_set is None else inliers_by_set[si])
+                                                    factor_inliers=None if inliers_by_set is None else inliers_by_set[si],
+                                                    factor_scale=None if scale_by_set is None else scale_by_set[si])
                 mine = [k for k in range(len(fset.factors)) if f_rank[k] == rank]
             else:
                 mine = list(range(len(fset.factors)))
@@ -608,6 +609,7 @@ def main():
             sw.set_poses(sub.deltas)
             sw._sub = sub
             sw._mine = mine
+            sw._f_rank = f_rank if sharded else None
             sweeps.append(sw)
             slabs.append(slab)
             my_pf += sw.point_factors
@@ -617,6 +619,7 @@ def main():
 
     sweeps, slabs, peers, my_pf, my_bytes, all_pf = make_sweeps()
     calibrated = False
+    feedback_history = []
     if sharded and world > 1:
         # Calibration sweep: a relinearizing back-end knows every factor's inlier count from its previous sweep; use it to
         # balance the partition by measured cost instead of the gate's overlap estimate, then rebuild this rank's sweeps.
@@ -635,6 +638,30 @@ def main():
         sweeps, slabs, peers, my_pf, my_bytes, all_pf = make_sweeps(inl, reuse_peers=peers if fused else None)
         del old
         calibrated = True
+        # Time feedback (<= 2 rounds): every rank times its own kernel (CUDA events, all ranks sweeping at once as in a step);
+        # the factors a rank held get their weight scaled by t_rank / mean(t) and the list is cut again.  A back-end that
+        # re-linearizes the same factor set every solver iteration gets these times for free.
+        scale = [np.ones(len(fs.factors)) for fs in w.sets]
+        for _ in range(2):
+            def kernels_only():
+                for sw in sweeps:
+                    sw.launch()
+            for _w in range(3):
+                kernels_only()
+            _, t_mine, _, _ = env.timed(kernels_only, 8, False)
+            t_all = np.array(env.gather_floats(t_mine), dtype=np.float64)
+            feedback_history.append([round(float(x) / 8, 4) for x in t_all])
+            if fused:
+                for sw, ps in zip(sweeps, peers):  # re-sync the exchange state after the kernel-only launches
+                    sw.launch()
+                    ps.signal_wait()
+            if t_all.max() <= 1.012 * t_all.mean():
+                break
+            for si, sw in enumerate(sweeps):
+                scale[si] *= (t_all / t_all.mean())[np.asarray(sw._f_rank)]
+            old = sweeps
+            sweeps, slabs, peers, my_pf, my_bytes, all_pf = make_sweeps(inl, reuse_peers=peers if fused else None, scale_by_set=scale)
+            del old
     total_pf = all_pf if sharded else all_pf * world  # replicas: every rank processes the whole stream
     ctx.synchronize()
 
@@ -764,7 +791,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.workload, w, {"parallelism": par,
-                                                       "tiles_grid_first_sweep": [int(sweeps[0].num_tiles), int(sweeps[0].grid)], "partition": ("contiguous, cost = n_source + 1.25 * measured inliers (calibration sweep)" if calibrated else "contiguous, cost = n_source * (1 + 1.25 * gate overlap)") if sharded else None, "build_seconds": round(build_s, 1), "scale": args.scale,
+                                                       "tiles_grid_first_sweep": [int(sweeps[0].num_tiles), int(sweeps[0].grid)], "partition": ("contiguous, cost = n_source + 1.25 * measured inliers (calibration sweep), then <= 2 rounds of per-rank kernel-time feedback" if calibrated else "contiguous, cost = n_source * (1 + 1.25 * gate overlap)") if sharded else None, "partition_feedback_kernel_ms": feedback_history or None, "build_seconds": round(build_s, 1), "scale": args.scale,
                                                        "kernel": os.environ.get("GB_KERNEL", "auto: k_vgicp_sweep5 + strided items for small sweeps, k_vgicp_sweep3 for large ones")}),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ems / e_steps,
                     "result": "pair slab (levels pre-summed on the device)" if sharded else "gb_linearized6 records"},

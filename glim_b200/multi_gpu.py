@@ -27,7 +27,7 @@ def lpt_partition(weights, n_parts: int):
     return part
 
 
-def shard_factors(factors, source_sizes, world: int, pair_cost=None, contiguous=True, factor_inliers=None):
+def shard_factors(factors, source_sizes, world: int, pair_cost=None, contiguous=True, factor_inliers=None, factor_scale=None):
     """factors: objects with .pair and .source, in the order the reference creates them (source-major: all factors of one
     new submap are consecutive, global_mapping.cpp:441-470); -> (rank per factor, rank per pair).  Pairs are kept whole.
 
@@ -36,6 +36,10 @@ def shard_factors(factors, source_sizes, world: int, pair_cost=None, contiguous=
 
     factor_inliers (optional): measured inlier count per factor from a previous sweep (a relinearizing back-end has them for
     free): the weight becomes n_source + 1.25 * inliers, which replaces the overlap estimate.
+
+    factor_scale (optional): multiplier per factor on top of either weight -- the time feedback of a back-end that re-linearizes
+    the same factor set many times: after a sweep every rank knows its kernel time t_r (CUDA events); the factors it held get
+    their weight scaled by t_r / mean(t), and the next partition evens out what the cost model missed (cache locality, ...).
 
     contiguous=True (default): cut the factor list into `world` consecutive chunks of equal total weight.  Every rank then
     keeps ALL factors of the source clouds it touches, so a source cloud is read from HBM once per rank-sweep and served from
@@ -50,11 +54,12 @@ def shard_factors(factors, source_sizes, world: int, pair_cost=None, contiguous=
     index = {p: k for k, p in enumerate(pairs)}
     w = np.zeros(len(pairs))
     for k, f in enumerate(factors):
+        sc = 1.0 if factor_scale is None else float(factor_scale[k])
         if factor_inliers is not None:
-            w[index[f.pair]] += source_sizes[f.source] + 1.25 * float(factor_inliers[k])
+            w[index[f.pair]] += sc * (source_sizes[f.source] + 1.25 * float(factor_inliers[k]))
         else:
             c = 1.0 + 1.25 * float(pair_cost[f.pair]) if pair_cost is not None and f.pair in pair_cost else 1.0
-            w[index[f.pair]] += source_sizes[f.source] * c
+            w[index[f.pair]] += sc * source_sizes[f.source] * c
     if contiguous:
         cum = np.cumsum(w) - 0.5 * w  # midpoint rule: a pair goes to the chunk its centre of mass falls in
         total = float(w.sum()) or 1.0

@@ -138,3 +138,31 @@ def test_contiguous_partition_is_balanced_ordered_and_keeps_sources_together():
     assert loads.max() <= loads.mean() * 1.02 + cost.max() * 2
     lpt, _ = multi_gpu.shard_factors(factors, sizes, 4, pair_cost=ov, contiguous=False)
     assert set(lpt) == {0, 1, 2, 3}
+
+
+def test_time_feedback_moves_work_off_the_slow_rank():
+    """bench.py's partition feedback: the factors of a rank that measured slow get heavier, the next cut gives it fewer."""
+    from glim_b200.workloads import Factor
+
+    rng = np.random.default_rng(5)
+    factors, pair = [], 0
+    for cur in range(1, 200):
+        for i in rng.choice(cur, size=min(cur, 6), replace=False):
+            for l in (0, 1):
+                factors.append(Factor(int(i), l, cur, pair))
+            pair += 1
+    sizes = [50000] * 200
+    inl = rng.uniform(1000, 40000, size=len(factors))
+    base, _ = multi_gpu.shard_factors(factors, sizes, 4, factor_inliers=inl)
+    t = np.array([1.08, 1.0, 1.0, 0.96])  # rank 0 measured 8 % slow, rank 3 fast
+    scale = (t / t.mean())[base]
+    fb, p_rank = multi_gpu.shard_factors(factors, sizes, 4, factor_inliers=inl, factor_scale=scale)
+    assert (np.diff(fb) >= 0).all() and set(fb) == {0, 1, 2, 3}
+    for f, r in zip(factors, fb):
+        assert r == p_rank[f.pair]
+    n0, n1 = np.bincount(base, minlength=4), np.bincount(fb, minlength=4)
+    assert n1[0] < n0[0] and n1[3] > n0[3]
+    # predicted times with the per-factor slowness carried along: the spread shrinks
+    cost = (np.array([sizes[f.source] for f in factors]) + 1.25 * inl) * scale
+    spread = lambda fr: np.ptp([cost[fr == r].sum() for r in range(4)])
+    assert spread(fb) < 0.5 * spread(base)
