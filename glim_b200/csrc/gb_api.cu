@@ -974,6 +974,10 @@ extern "C" gb_status gb_peer_slab_create(gb_ctx* ctx, size_t num_pairs, int worl
   ps->ctx = ctx; ps->num_pairs = num_pairs; ps->world = world; ps->rank = rank;
   ps->buf_floats = align_up(num_pairs * GB_SLAB_STRIDE * sizeof(float), 256) / sizeof(float);
   ps->local = nullptr; ps->step = 0; ps->parity = 0; ps->completed_parity = 0; ps->d_timeout = nullptr; ps->connected = (world == 1);
+  // GB_PEER_PUSH=fused: the sweep's epilogue stores every finished row straight into all peers (round-1 design); default:
+  // deferred -- rows go to the local buffer and the exchange kernel pushes them (see gb_launch_peer_signal_wait)
+  { const char* e = getenv("GB_PEER_PUSH"); ps->deferred = !(e && !strcmp(e, "fused")); }
+  ps->d_my_pairs = nullptr; ps->num_my_pairs = 0;
   for (int p = 0; p < GB_MAX_PEERS; p++) { ps->peer[p] = nullptr; ps->opened[p] = false; }
   const size_t bytes = peer_alloc_bytes(num_pairs, world);
   cudaError_t e = cudaMalloc((void**)&ps->local, bytes + 256);
@@ -1023,6 +1027,7 @@ extern "C" gb_status gb_peer_slab_destroy(gb_peer_slab* ps) {
   for (int p = 0; p < ps->world; p++)
     if (ps->opened[p]) cudaIpcCloseMemHandle(ps->peer[p]);
   if (ps->local) cudaFree(ps->local);
+  if (ps->d_my_pairs) cudaFree(ps->d_my_pairs);
   if (ps->h_pinned) cudaFreeHost(ps->h_pinned);
   gb_ctx* ctx = ps->ctx;
   delete ps;
@@ -1056,14 +1061,28 @@ extern "C" gb_status gb_sweep_attach_peer_slab(gb_sweep* s, gb_peer_slab* ps) {
   PeerPush tabs[2];
   memset(tabs, 0, sizeof(tabs));
   for (int par = 0; par < 2; par++) {
-    tabs[par].world = ps->world;
-    for (int p = 0; p < ps->world; p++) tabs[par].base[p] = reinterpret_cast<float*>(ps->peer[p]) + (size_t)par * ps->buf_floats;
+    if (ps->deferred) {  // the sweep writes this rank's buffer only
+      tabs[par].world = 1;
+      tabs[par].base[0] = reinterpret_cast<float*>(ps->local) + (size_t)par * ps->buf_floats;
+    } else {
+      tabs[par].world = ps->world;
+      for (int p = 0; p < ps->world; p++) tabs[par].base[p] = reinterpret_cast<float*>(ps->peer[p]) + (size_t)par * ps->buf_floats;
+    }
     tabs[par].pair_ptr = s->d_pair_ptr; tabs[par].pair_factors = s->d_pair_factors; tabs[par].pair_done = s->d_pair_done;
   }
   GB_CUDA(cudaMemcpy(s->d_peer_tables, tabs, sizeof(tabs), cudaMemcpyHostToDevice));
   GB_CUDA(cudaMemcpy(s->d_pair_ptr, ptr.data(), sizeof(int) * (P + 1), cudaMemcpyHostToDevice));
   if (s->F) GB_CUDA(cudaMemcpy(s->d_pair_factors, fac.data(), sizeof(int) * s->F, cudaMemcpyHostToDevice));
   GB_CUDA(cudaMemset(s->d_pair_done, 0, b_done));
+  // the pairs this sweep owns (one sweep per peer slab): the rows the exchange kernel copies to the peers
+  std::vector<int> mine;
+  for (size_t k = 0; k < P; k++) if (ptr[k + 1] > ptr[k]) mine.push_back((int)k);
+  if (ps->d_my_pairs) { GB_CUDA(cudaFree(ps->d_my_pairs)); ps->d_my_pairs = nullptr; }
+  ps->num_my_pairs = (int)mine.size();
+  if (!mine.empty()) {
+    GB_CUDA(cudaMalloc((void**)&ps->d_my_pairs, sizeof(int) * mine.size()));
+    GB_CUDA(cudaMemcpy(ps->d_my_pairs, mine.data(), sizeof(int) * mine.size(), cudaMemcpyHostToDevice));
+  }
   s->peer = ps;
   return GB_OK;
 }

@@ -123,6 +123,11 @@ struct gb_peer_slab {
   int* d_timeout;
   float* h_pinned;                // num_pairs x GB_SLAB_STRIDE, for the fetches
   bool connected;
+  // deferred exchange (default): the sweep stores finished pair rows into the LOCAL buffer only; the exchange kernel that
+  // follows it copies this rank's rows to every peer (one CTA per peer) before it publishes the completion flags
+  bool deferred;
+  int* d_my_pairs;                // pair ids owned by the attached sweep
+  int num_my_pairs;
 };
 
 #define GB_ACC_STRIDE 32      // doubles per factor in the accumulation buffer (29 used)

@@ -1146,7 +1146,61 @@ gb_status gb_launch_sweep(gb_sweep* s, int mode) {
   return GB_OK;
 }
 
+// Deferred exchange: CTA p copies this rank's finished rows (written by the sweep into the local buffer of the step
+// parity) into peer p's buffer -- 128-bit stores through the IPC mapping, ~164 KB per peer at 8 ranks -- then publishes this
+// rank's step to that peer and waits for the peer's flag.  The CTAs are independent (one per peer): no ordering between them.
+// Why not from the sweep's epilogue (GB_PEER_PUSH=fused, the round-1 design): stores to peer memory issued from the 148 busy
+// SMs cost the sweep 3.5-6 % at 8 ranks (profiles/r02_bench_n8_*.json: per-rank kernel 0.398 ms fused against 0.374 ms for the
+// same shard without the peer stores) while the whole exchange is ~1 MB per rank and step.
+struct PeerExchange {
+  float* dst[GB_MAX_PEERS];   // every rank's buffer of the step parity, as mapped here
+  unsigned* flags[GB_MAX_PEERS];
+  const float* src;           // this rank's buffer of the step parity
+  const int* my_pairs;
+  int num_my_pairs;
+};
+__global__ void __launch_bounds__(256) k_peer_exchange(PeerExchange px, int world, int rank, unsigned step, int* timeout) {
+  const int p = blockIdx.x;
+  if (p != rank) {
+    float4* __restrict__ dst = reinterpret_cast<float4*>(px.dst[p]);
+    const float4* __restrict__ src = reinterpret_cast<const float4*>(px.src);
+    constexpr int kVec = GB_SLAB_STRIDE / 4;
+    const int total = px.num_my_pairs * kVec;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const size_t at = (size_t)px.my_pairs[e / kVec] * kVec + (size_t)(e % kVec);
+      dst[at] = src[at];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  volatile unsigned* remote = px.flags[p] + rank;
+  *remote = step;
+  volatile unsigned* mine = px.flags[rank] + p;
+  const long long t0 = clock64();
+  while ((int)(*mine - step) < 0) {
+    __nanosleep(100);
+    if (clock64() - t0 > 4000000000ll) { *timeout = 1; break; }  // ~2 s: a peer died; do not hold the GPU
+  }
+  __threadfence_system();
+}
+
 gb_status gb_launch_peer_signal_wait(gb_peer_slab* ps) {
+  if (ps->deferred) {
+    PeerExchange px;
+    memset(&px, 0, sizeof(px));
+    for (int p = 0; p < ps->world; p++) {
+      px.dst[p] = reinterpret_cast<float*>(ps->peer[p]) + (size_t)ps->parity * ps->buf_floats;
+      px.flags[p] = reinterpret_cast<unsigned*>(ps->peer[p] + 2 * ps->buf_floats * sizeof(float));
+    }
+    px.src = reinterpret_cast<const float*>(ps->local) + (size_t)ps->parity * ps->buf_floats;
+    px.my_pairs = ps->d_my_pairs;
+    px.num_my_pairs = ps->num_my_pairs;
+    k_peer_exchange<<<ps->world, 256, 0, ps->ctx->stream>>>(px, ps->world, ps->rank, ps->step, ps->d_timeout);
+    GB_CUDA(cudaGetLastError());
+    ps->ctx->launches++;
+    return GB_OK;
+  }
   PeerFlags pf;
   memset(&pf, 0, sizeof(pf));
   for (int p = 0; p < ps->world; p++) pf.flags[p] = reinterpret_cast<unsigned*>(ps->peer[p] + 2 * ps->buf_floats * sizeof(float));
