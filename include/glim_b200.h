@@ -158,14 +158,16 @@ GB_API gb_status gb_sweep_results_device(gb_sweep* sweep, void** device_ptr);   
 /* bookkeeping for the roofline: sum of N_source, and algorithmic bytes B_sweep of SURVEY 8(d) */
 GB_API gb_status gb_sweep_stats(const gb_sweep* sweep, uint64_t* point_factors, uint64_t* algorithmic_bytes, uint32_t* num_tiles, uint32_t* grid_size);
 
-/* ---- Multi-GPU result exchange fused into the sweep (no reference counterpart: GLIM is single-GPU).
+/* ---- Multi-GPU result exchange (no reference counterpart: GLIM is single-GPU).
  *      A gb_peer_slab is a pair of fp32 buffers [num_pairs][GB_SLAB_STRIDE] (ping-pong by step parity) plus completion
  *      flags, allocated with cudaMalloc and shared with the other ranks of the box through CUDA IPC.  When one is attached
- *      to a sweep, the epilogue of the LAST factor of every pair sums the pair's factor records in fp64 and stores the
- *      finished row with 128-bit stores straight into EVERY rank's buffer over NVLink (each pair is owned by exactly one
- *      rank, so the "all-reduce" is an all-gather done by the producers); gb_peer_slab_signal_wait() then publishes this
- *      rank's completion flag to all peers and waits for theirs.  No NCCL call, no memset, no float atomics (rows are
- *      deterministic).  With world == 1 it is simply the deterministic way to get the pair slab. ---- */
+ *      to a sweep (ONE sweep per slab), the epilogue of the LAST factor of every pair sums the pair's factor records in fp64
+ *      and stores the finished row into this rank's buffer; gb_peer_slab_signal_wait() launches the exchange kernel: one
+ *      CTA per peer copies the rank's rows into that peer's buffer over NVLink, publishes this rank's completion flag and
+ *      waits for the peer's (each pair is owned by exactly one rank, so the "all-reduce" is an all-gather done by the
+ *      producers).  No NCCL call, no memset, no float atomics (rows are deterministic).  With world == 1 it is simply the
+ *      deterministic way to get the pair slab.  GB_PEER_PUSH=fused in the environment selects the round-1 variant (rows
+ *      stored straight into every peer from the sweep's epilogue; measured slower at 8 ranks). ---- */
 #define GB_IPC_HANDLE_BYTES 64
 typedef struct gb_peer_slab gb_peer_slab;
 GB_API gb_status gb_peer_slab_create(gb_ctx* ctx, size_t num_pairs, int world, int rank, gb_peer_slab** out);
