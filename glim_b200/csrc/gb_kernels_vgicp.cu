@@ -1150,7 +1150,7 @@ gb_status gb_launch_sweep(gb_sweep* s, int mode) {
 // parity) into peer p's buffer -- 128-bit stores through the IPC mapping, ~164 KB per peer at 8 ranks -- then publishes this
 // rank's step to that peer and waits for the peer's flag.  The CTAs are independent (one per peer): no ordering between them.
 // Why not from the sweep's epilogue (GB_PEER_PUSH=fused, the round-1 design): stores to peer memory issued from the 148 busy
-// SMs cost the sweep 3.5-6 % at 8 ranks (profiles/r02_bench_n8_*.json: per-rank kernel 0.398 ms fused against 0.374 ms for the
+// SMs cost the sweep 3.5-6 % at 8 ranks (profiles/r02_bench_n8_fused_push*.json, r02_bench_n8_nccl.json: per-rank kernel 0.398 ms fused against 0.374 ms for the
 // same shard without the peer stores) while the whole exchange is ~1 MB per rank and step.
 struct PeerExchange {
   float* dst[GB_MAX_PEERS];   // every rank's buffer of the step parity, as mapped here
