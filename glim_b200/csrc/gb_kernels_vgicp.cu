@@ -1146,7 +1146,7 @@ gb_status gb_launch_sweep(gb_sweep* s, int mode) {
   return GB_OK;
 }
 
-// Deferred exchange: CTA p copies this rank's finished rows (written by the sweep into the local buffer of the step
+// Deferred exchange: the four CTAs of peer p copy this rank's finished rows (written by the sweep into the local buffer of the step
 // parity) into peer p's buffer -- 128-bit stores through the IPC mapping, ~164 KB per peer at 8 ranks -- then publishes this
 // rank's step to that peer and waits for the peer's flag.  The CTAs are independent (one per peer): no ordering between them.
 // Why not from the sweep's epilogue (GB_PEER_PUSH=fused, the round-1 design): stores to peer memory issued from the 148 busy
@@ -1158,22 +1158,41 @@ struct PeerExchange {
   const float* src;           // this rank's buffer of the step parity
   const int* my_pairs;
   int num_my_pairs;
+  unsigned* arrivals;         // [world] CTA arrival counters (self-cleaning)
 };
-__global__ void __launch_bounds__(256) k_peer_exchange(PeerExchange px, int world, int rank, unsigned step, int* timeout) {
-  const int p = blockIdx.x;
+constexpr int kExchangeCtasPerPeer = 4;
+constexpr int kExchangeThreads = 512;
+__global__ void __launch_bounds__(kExchangeThreads) k_peer_exchange(PeerExchange px, int world, int rank, unsigned step, int* timeout) {
+  const int p = blockIdx.x / kExchangeCtasPerPeer, c = blockIdx.x % kExchangeCtasPerPeer;
   if (p != rank) {
     float4* __restrict__ dst = reinterpret_cast<float4*>(px.dst[p]);
     const float4* __restrict__ src = reinterpret_cast<const float4*>(px.src);
     constexpr int kVec = GB_SLAB_STRIDE / 4;
     const int total = px.num_my_pairs * kVec;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-      const size_t at = (size_t)px.my_pairs[e / kVec] * kVec + (size_t)(e % kVec);
-      dst[at] = src[at];
+    const int stride = kExchangeCtasPerPeer * kExchangeThreads;
+    // four independent 16-byte loads in flight per thread: the copy is latency-, not bandwidth-bound (~1 MB per rank and step)
+    for (int e0 = c * kExchangeThreads + threadIdx.x; e0 < total; e0 += 4 * stride) {
+      float4 v[4];
+      size_t at[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = min(e0 + u * stride, total - 1);
+        at[u] = (size_t)px.my_pairs[e / kVec] * kVec + (size_t)(e % kVec);
+        v[u] = __ldcg(&src[at[u]]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (e0 + u * stride < total) dst[at[u]] = v[u];
     }
   }
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x != 0) return;
+  // the last of this peer's CTAs publishes the flag and waits for the peer's
+  const unsigned arrived = atomicAdd(&px.arrivals[p], 1u);
+  if (arrived != (unsigned)kExchangeCtasPerPeer - 1u) return;
+  px.arrivals[p] = 0u;
+  __threadfence_system();
   volatile unsigned* remote = px.flags[p] + rank;
   *remote = step;
   volatile unsigned* mine = px.flags[rank] + p;
@@ -1196,7 +1215,8 @@ gb_status gb_launch_peer_signal_wait(gb_peer_slab* ps) {
     px.src = reinterpret_cast<const float*>(ps->local) + (size_t)ps->parity * ps->buf_floats;
     px.my_pairs = ps->d_my_pairs;
     px.num_my_pairs = ps->num_my_pairs;
-    k_peer_exchange<<<ps->world, 256, 0, ps->ctx->stream>>>(px, ps->world, ps->rank, ps->step, ps->d_timeout);
+    px.arrivals = reinterpret_cast<unsigned*>(ps->d_timeout) + 16;  // zeroed at creation, self-cleaning
+    k_peer_exchange<<<ps->world * kExchangeCtasPerPeer, kExchangeThreads, 0, ps->ctx->stream>>>(px, ps->world, ps->rank, ps->step, ps->d_timeout);
     GB_CUDA(cudaGetLastError());
     ps->ctx->launches++;
     return GB_OK;
