@@ -785,7 +785,7 @@ def main():
 
     line = None
     if rank == 0:
-        push_fused = os.environ.get("GB_PEER_PUSH") == "fused"
+        push_fused = os.environ.get("GB_PEER_PUSH") == "fused" or (os.environ.get("GB_PEER_PUSH") != "deferred" and world <= 4)  # the library's policy
         how = ("are stored into every rank's buffer by the sweep kernel's epilogue over NVLink (CUDA IPC peer memory) + completion flags" if push_fused else
                "are written to the rank's own buffer by the sweep kernel's epilogue; the exchange kernel that follows (four CTAs per peer) copies the rank's rows into every peer's buffer over NVLink (CUDA IPC peer memory) and publishes / awaits the completion flags")
         par = (f"pairs sharded over {world} rank(s); finished pair rows of the [{peers[0].num_pairs} x {GB_SLAB_STRIDE}] fp32 Hessian slab {how}; no NCCL in the step"

@@ -974,9 +974,16 @@ extern "C" gb_status gb_peer_slab_create(gb_ctx* ctx, size_t num_pairs, int worl
   ps->ctx = ctx; ps->num_pairs = num_pairs; ps->world = world; ps->rank = rank;
   ps->buf_floats = align_up(num_pairs * GB_SLAB_STRIDE * sizeof(float), 256) / sizeof(float);
   ps->local = nullptr; ps->step = 0; ps->parity = 0; ps->completed_parity = 0; ps->d_timeout = nullptr; ps->connected = (world == 1);
-  // GB_PEER_PUSH=fused: the sweep's epilogue stores every finished row straight into all peers (round-1 design); default:
-  // deferred -- rows go to the local buffer and the exchange kernel pushes them (see gb_launch_peer_signal_wait)
-  { const char* e = getenv("GB_PEER_PUSH"); ps->deferred = !(e && !strcmp(e, "fused")); }
+  // fused: the sweep's epilogue stores every finished row straight into all peers; deferred: rows go to the local buffer and
+  // the exchange kernel pushes them (see gb_launch_peer_signal_wait).  Measured: the peer stores cost the
+  // sweep ~5 us at 4 ranks and ~13 us at 8, the exchange kernel is 5-9 us longer than the flag-only one -> fused up to 4
+  // ranks, deferred above.  GB_PEER_PUSH=fused|deferred forces one.
+  {
+    const char* e = getenv("GB_PEER_PUSH");
+    ps->deferred = world > 4;
+    if (e && !strcmp(e, "fused")) ps->deferred = false;
+    if (e && !strcmp(e, "deferred")) ps->deferred = true;
+  }
   ps->d_my_pairs = nullptr; ps->num_my_pairs = 0;
   for (int p = 0; p < GB_MAX_PEERS; p++) { ps->peer[p] = nullptr; ps->opened[p] = false; }
   const size_t bytes = peer_alloc_bytes(num_pairs, world);

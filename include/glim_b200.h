@@ -162,12 +162,13 @@ GB_API gb_status gb_sweep_stats(const gb_sweep* sweep, uint64_t* point_factors, 
  *      A gb_peer_slab is a pair of fp32 buffers [num_pairs][GB_SLAB_STRIDE] (ping-pong by step parity) plus completion
  *      flags, allocated with cudaMalloc and shared with the other ranks of the box through CUDA IPC.  When one is attached
  *      to a sweep (ONE sweep per slab), the epilogue of the LAST factor of every pair sums the pair's factor records in fp64
- *      and stores the finished row into this rank's buffer; gb_peer_slab_signal_wait() launches the exchange kernel: one
- *      CTA per peer copies the rank's rows into that peer's buffer over NVLink, publishes this rank's completion flag and
- *      waits for the peer's (each pair is owned by exactly one rank, so the "all-reduce" is an all-gather done by the
- *      producers).  No NCCL call, no memset, no float atomics (rows are deterministic).  With world == 1 it is simply the
- *      deterministic way to get the pair slab.  GB_PEER_PUSH=fused in the environment selects the round-1 variant (rows
- *      stored straight into every peer from the sweep's epilogue; measured slower at 8 ranks). ---- */
+ *      and stores the finished row -- up to 4 ranks straight into EVERY rank's buffer over NVLink (fused push), above 4 ranks
+ *      into this rank's buffer only (deferred push: stores to peer memory from the busy SMs cost the sweep 3.5-6 % at 8
+ *      ranks).  gb_peer_slab_signal_wait() launches the kernel that (deferred push only: four CTAs per
+ *      peer) copies the rank's rows into that peer's buffer, publishes this rank's completion flag and waits for the peers'.
+ *      Each pair is owned by exactly one rank, so the "all-reduce" is an all-gather done by the producers.  No NCCL call, no
+ *      memset, no float atomics (rows are deterministic).  With world == 1 it is simply the deterministic way to get the
+ *      pair slab.  GB_PEER_PUSH=fused|deferred in the environment forces one variant. ---- */
 #define GB_IPC_HANDLE_BYTES 64
 typedef struct gb_peer_slab gb_peer_slab;
 GB_API gb_status gb_peer_slab_create(gb_ctx* ctx, size_t num_pairs, int world, int rank, gb_peer_slab** out);
