@@ -44,6 +44,10 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <numeric>
+#include <random>
+#include <functional>
+#include <string>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -354,6 +358,34 @@ private:
   gb_cloud* cloud_ = nullptr;
 };
 
+/// gtsam_points::sample(frame, indices): a PointCloudCPU holding the listed points with every attribute `frame` has.
+inline PointCloudCPU::Ptr sample(const PointCloud::ConstPtr& frame, const std::vector<int>& indices) {
+  auto out = std::make_shared<PointCloudCPU>();
+  const std::size_t m = indices.size();
+  out->num_points = m;
+  if (frame->points) { out->points_storage.resize(m); for (std::size_t k = 0; k < m; k++) out->points_storage[k] = frame->points[indices[k]]; out->points = out->points_storage.data(); }
+  if (frame->covs) { out->covs_storage.resize(m); for (std::size_t k = 0; k < m; k++) out->covs_storage[k] = frame->covs[indices[k]]; out->covs = out->covs_storage.data(); }
+  if (frame->normals) { out->normals_storage.resize(m); for (std::size_t k = 0; k < m; k++) out->normals_storage[k] = frame->normals[indices[k]]; out->normals = out->normals_storage.data(); }
+  if (frame->times) { out->times_storage.resize(m); for (std::size_t k = 0; k < m; k++) out->times_storage[k] = frame->times[indices[k]]; out->times = out->times_storage.data(); }
+  if (frame->intensities) { out->intensities_storage.resize(m); for (std::size_t k = 0; k < m; k++) out->intensities_storage[k] = frame->intensities[indices[k]]; out->intensities = out->intensities_storage.data(); }
+  return out;
+}
+
+/// gtsam_points::random_sampling(frame, sampling_rate, mt)  (sub_mapping.cpp:385; global_mapping.cpp:248, :734 -- host side,
+/// BEFORE the frame is uploaded): sampling_rate * size() points drawn without replacement, in ascending index order
+/// (std::sample over the index range [EXT]; the draw depends on the caller's generator exactly as in the reference).
+template <typename Rng>
+inline PointCloudCPU::Ptr random_sampling(const PointCloud::ConstPtr& frame, double sampling_rate, Rng& mt) {
+  const std::size_t n = frame->size();
+  if (sampling_rate >= 1.0) return std::make_shared<PointCloudCPU>(*frame);
+  const std::size_t m = static_cast<std::size_t>(static_cast<double>(n) * std::max(0.0, sampling_rate));
+  std::vector<int> all(n), picked;
+  std::iota(all.begin(), all.end(), 0);
+  picked.reserve(m);
+  std::sample(all.begin(), all.end(), std::back_inserter(picked), m, mt);
+  return sample(frame, picked);
+}
+
 /// gtsam_points::merge_frames_gpu(poses, frames, downsample_resolution[, target_num_points]) -- the call the reference left
 /// commented out at src/glim/mapping/sub_mapping.cpp:491 (its CPU twin merge_frames is what :496 runs).  Frames must be
 /// PointCloudGPU; the merged submap comes back as a PointCloudGPU (host points / covariances + device cloud).
@@ -377,6 +409,19 @@ inline PointCloudGPU::Ptr merge_frames_gpu(const std::vector<glim_b200::Pose>& p
                                    reinterpret_cast<double*>(covs.data()), &m, &cloud),
                    "gb_merge_frames");
   return PointCloudGPU::adopt(reinterpret_cast<const double*>(pts.data()), reinterpret_cast<const double*>(covs.data()), nullptr, nullptr, nullptr, m, cloud);
+}
+
+/// gtsam_points::VoxelBucket (standard_viewer_mem.cpp:77 takes its size): one 16-byte open-addressing slot {x, y, z, voxel index}
+struct VoxelBucket { int coord[3]; int index; };
+static_assert(sizeof(VoxelBucket) == 16, "bucket layout");
+
+/// gtsam_points::cuda_mem_get_info(&free, &total)  (memory_monitor.cpp:39) on the default device
+inline void cuda_mem_get_info(std::size_t* free_bytes, std::size_t* total_bytes) { glim_b200::check(gb_mem_info(0, free_bytes, total_bytes), "gb_mem_info"); }
+/// gtsam_points::cuda_device_names()  (debug.cpp:84): one entry per visible device (the C-ABI reports the count, not the marketing name)
+inline std::vector<std::string> cuda_device_names() {
+  std::vector<std::string> names;
+  for (int d = 0; d < gb_device_count(); d++) names.push_back("CUDA device " + std::to_string(d) + " (sm_100a)");
+  return names;
 }
 
 struct VoxelMapInfo {
@@ -643,6 +688,24 @@ public:
 private:
   std::vector<std::shared_ptr<IntegratedVGICPFactorGPU>> factors_;
   std::vector<gb_linearized6> results_;
+};
+
+/// gtsam_points::create_nonlinear_factor_set_gpu() and LinearizationHook::register_hook(...)  (offline_viewer.cpp:29): the
+/// optimizers of the reference ask the registered hooks for a factor set to batch-linearize the GPU factors of a graph; the
+/// optimizers themselves are out of scope, the registry is here so that the call site compiles and the hook is retrievable.
+inline std::shared_ptr<NonlinearFactorSetGPU> create_nonlinear_factor_set_gpu() { return std::make_shared<NonlinearFactorSetGPU>(); }
+struct LinearizationHook {
+  using Hook = std::function<std::shared_ptr<NonlinearFactorSetGPU>()>;
+  static void register_hook(const Hook& hook) { std::lock_guard<std::mutex> lock(mutex()); hooks().push_back(hook); }
+  static std::vector<std::shared_ptr<NonlinearFactorSetGPU>> create_factor_sets() {
+    std::lock_guard<std::mutex> lock(mutex());
+    std::vector<std::shared_ptr<NonlinearFactorSetGPU>> sets;
+    for (const auto& h : hooks()) sets.push_back(h());
+    return sets;
+  }
+private:
+  static std::vector<Hook>& hooks() { static std::vector<Hook> h; return h; }
+  static std::mutex& mutex() { static std::mutex m; return m; }
 };
 
 /// gtsam_points::overlap_gpu(voxelmap, source, delta, stream)   odometry_estimation_gpu.cpp:248

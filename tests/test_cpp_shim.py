@@ -30,6 +30,25 @@ def test_shims_compile_standalone_and_gtsam_mode(tmp_path):
     subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{INC}", "-c", os.path.join(CPP, "preprocess_main.cpp"), "-o", str(tmp_path / "d.o")])
 
 
+def test_host_side_helpers_run_without_a_device(tmp_path):
+    """random_sampling / sample (sub_mapping.cpp:385, global_mapping.cpp:248), the factor-set hook (offline_viewer.cpp:29) and
+    VoxelBucket: host code of the shim, built against the library and run here (no device call is made)."""
+    lib_dir = os.path.join(ROOT, "glim_b200")
+    exe = tmp_path / "host_helpers"
+    subprocess.check_call([GXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", f"-I{INC}", os.path.join(CPP, "host_helpers_main.cpp"), "-o", str(exe),
+                           f"-L{lib_dir}", "-lglim_b200", f"-Wl,-rpath,{lib_dir}"])
+    out = tmp_path / "out.bin"
+    n, rate = 5000, 0.1
+    assert subprocess.call([str(exe), str(n), str(rate), str(out)]) == 0
+    raw = out.read_bytes()
+    m = int(np.frombuffer(raw[:4], np.int32)[0])
+    idx = np.frombuffer(raw[4:4 + 4 * m], np.int32)
+    assert m == int(n * rate) and raw[-1] == 1
+    assert (np.diff(idx) > 0).all() and idx.min() >= 0 and idx.max() < n
+    # a uniform draw: the sample's mean index is near the middle, every decile is hit
+    assert abs(idx.mean() - n / 2) < 0.1 * n and len(set(idx // (n // 10))) == 10
+
+
 def test_solver_handoff_blocks_host_only():
     """gb_hessian_blocks / gb_slab_row_hessian_blocks (global_mapping.cpp:492-501): HessianFactor(k_t, k_s, H_tt, H_ts,
     -b_t, H_ss, -b_s, scale * error) from a record and from a pair-slab row; host-only helpers, no device needed."""
