@@ -411,6 +411,15 @@ inline PointCloudGPU::Ptr merge_frames_gpu(const std::vector<glim_b200::Pose>& p
   return PointCloudGPU::adopt(reinterpret_cast<const double*>(pts.data()), reinterpret_cast<const double*>(covs.data()), nullptr, nullptr, nullptr, m, cloud);
 }
 
+/// gtsam_points::merge_frames(poses, frames, downsample_resolution, target_num_points)  (sub_mapping.cpp:496, the call that
+/// runs today): with GPU keyframes -- what params.enable_gpu produces at sub_mapping.cpp:393 -- it is merge_frames_gpu.
+/// There is no CPU path in this library: host-only frames are rejected.
+inline PointCloud::Ptr merge_frames(const std::vector<glim_b200::Pose>& poses, const std::vector<PointCloud::ConstPtr>& frames, double downsample_resolution, int target_num_points = 0) {
+  for (const auto& f : frames)
+    if (!std::dynamic_pointer_cast<const PointCloudGPU>(f)) throw std::runtime_error("merge_frames: frames must be PointCloudGPU (clone them first); libglim_b200 has no CPU path");
+  return merge_frames_gpu(poses, frames, downsample_resolution, target_num_points);
+}
+
 /// gtsam_points::VoxelBucket (standard_viewer_mem.cpp:77 takes its size): one 16-byte open-addressing slot {x, y, z, voxel index}
 struct VoxelBucket { int coord[3]; int index; };
 static_assert(sizeof(VoxelBucket) == 16, "bucket layout");

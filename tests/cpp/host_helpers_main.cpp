@@ -50,6 +50,12 @@ int main(int argc, char** argv) {
   const auto sets = LinearizationHook::create_factor_sets();
   ok = ok && sets.size() == 1 && sets[0] && sets[0]->size() == 0;
   ok = ok && sizeof(VoxelBucket) == 16;
+  // merge_frames (sub_mapping.cpp:496) refuses host-only frames instead of falling back to a CPU path
+  try {
+    merge_frames({glim_b200::Pose()}, {frame}, 0.5, 0);
+    ok = false;
+  } catch (const std::runtime_error&) {
+  }
 
   FILE* fo = fopen(argv[3], "wb");
   const int m = (int)idx.size();
