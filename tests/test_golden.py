@@ -72,3 +72,24 @@ def test_gpu_reproduces_golden(ctx):
     assert np.allclose(cv, G["covs0"], atol=1e-9)
     vg, vt, _ = preprocess.voxelgrid_sampling(G["points0"], 0.3, times=G["times0"], ctx=ctx)
     assert np.array_equal(vg, G["voxelgrid_points"]) and np.array_equal(vt, G["voxelgrid_times"])
+
+
+def test_oracle_reproduces_round2_golden():
+    """random grid, merge_frames and the surface-validation gate (tests/golden/make_golden_round2.py): exact."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden_round2", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden_round2.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "round2_golden.npz"))
+    now = mod.compute(G)
+    assert set(now) == set(G2.files)
+    for k in G2.files:
+        if k in ("sv_linearized", "normals1"):
+            assert np.allclose(now[k], G2[k], rtol=1e-12, atol=1e-9), k
+        else:
+            assert np.array_equal(now[k], G2[k]), k
+    # sanity of what was frozen: the gate rejects some but not all correspondences; thinning halves the merged cloud
+    assert 0 < (G2["sv_corr"] == -2).sum() < (G2["sv_corr"] != -1).sum()
+    assert len(G2["merge_thinned_points"]) == len(G2["merge_points"]) // 2
+    assert 0 < len(G2["randomgrid_keep_r100_rate030_seed5"]) <= int(len(G["points0"]) * 0.3 * 1.2)
