@@ -229,12 +229,7 @@ gb_status gb_voxelgrid_sampling_impl(gb_ctx* ctx, size_t n, const double* xyzw, 
 // device helpers shared by kernels
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
-// canonical voxel coordinate (fp32): floorf(p * inv_res); oracle: voxel_coord_f32 (glim_oracle.c)
-__device__ __forceinline__ int gb_coord(float p, float inv_res) { return __float2int_rd(p * inv_res); }
-// XOR-of-primes hash; low 32 bits == the u64 evaluation modulo a power-of-two table
-__device__ __forceinline__ uint32_t gb_hash(int x, int y, int z) {
-  return ((uint32_t)x * 73856093u) ^ ((uint32_t)y * 19349669u) ^ ((uint32_t)z * 83492791u);
-}
+#include "gb_vgicp_math.cuh"  // gb_coord, gb_hash (shared with the host-compiled CPU test of the kernel arithmetic)
 // packed 3 x 21-bit voxel key (ascending key = canonical voxel order); false if out of range
 #define GB_KEY_OFFSET (1 << 20)
 __device__ __forceinline__ bool gb_pack_key(int x, int y, int z, unsigned long long* key) {
