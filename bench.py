@@ -67,6 +67,18 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def cpu_model():
+    """CPU model string of the host (state the host the CPU arm ran on, never assume it)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------------------------------------------
 # workload construction (identical on every rank: seeded)
 # --------------------------------------------------------------------------------------------------------------
@@ -238,7 +250,7 @@ def cpu_thread_sweep(s, seconds):
 def cpu_baseline(w, seconds):
     s = CpuSample.from_workload(w)
     best, per = cpu_thread_sweep(s, seconds)
-    return {"value": per[best], "unit": UNIT, "cores": best, "kind": "port", "host_threads_available": s.threads,
+    return {"value": per[best], "unit": UNIT, "cores": best, "kind": "port", "host_threads_available": s.threads, "cpu_model": cpu_model(),
             "by_threads": {str(t): round(v, 2) for t, v in per.items()},
             "sample": f"{s.desc}; ~{seconds:.0f} s of CPU work split over thread counts {sorted(per)}; fp64, update_correspondences + evaluate (OpenMP); value = fastest thread count ({best})"}
 
@@ -318,7 +330,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": best, "kind": "port", "host_threads_available": s.threads, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": best, "kind": "port", "host_threads_available": s.threads, "cpu_model": cpu_model(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
                          "by_threads": {str(t): round(v, 2) for t, v in per.items()},
                          "sample": s.desc + f"; one step = one pass over the sample with the fastest thread count ({best}); thread count from sched_getaffinity, OMP_NUM_THREADS ignored"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
