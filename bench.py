@@ -230,18 +230,24 @@ def cpu_thread_sweep(s, seconds):
     cands = sorted({t for t in (2, 8, 16, 32, allt) if t <= allt})
     per = {}
     budget = seconds / len(cands)
+    s.spread = {}
     for t in cands:
         s.set_threads(t)
         s.run_once()
         t0 = time.perf_counter()
-        reps = 0
+        reps, laps, last = 0, [], t0
         while True:
             s.run_once()
             reps += 1
-            el = time.perf_counter() - t0
+            now = time.perf_counter()
+            laps.append(now - last)
+            last = now
+            el = now - t0
             if el >= budget or reps >= 100000:
                 break
         per[t] = s.point_factors * reps / el / 1e6
+        q = np.percentile(np.asarray(laps), [90, 50, 10])  # slow laps = low throughput: p10 of the throughput is the p90 lap
+        s.spread[t] = [round(float(s.point_factors / x / 1e6), 2) for x in q]
     best = max(per, key=lambda t: per[t])
     s.set_threads(best)
     return best, per
@@ -251,7 +257,7 @@ def cpu_baseline(w, seconds):
     s = CpuSample.from_workload(w)
     best, per = cpu_thread_sweep(s, seconds)
     return {"value": per[best], "unit": UNIT, "cores": best, "kind": "port", "host_threads_available": s.threads, "cpu_model": cpu_model(),
-            "by_threads": {str(t): round(v, 2) for t, v in per.items()},
+            "by_threads": {str(t): round(v, 2) for t, v in per.items()}, "p10_median_p90_at_best": s.spread.get(best),
             "sample": f"{s.desc}; ~{seconds:.0f} s of CPU work split over thread counts {sorted(per)}; fp64, update_correspondences + evaluate (OpenMP); value = fastest thread count ({best})"}
 
 
@@ -331,7 +337,7 @@ def run_reference(args, rank):
         "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": best, "kind": "port", "host_threads_available": s.threads, "cpu_model": cpu_model(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
-                         "by_threads": {str(t): round(v, 2) for t, v in per.items()},
+                         "by_threads": {str(t): round(v, 2) for t, v in per.items()}, "p10_median_p90_at_best": s.spread.get(best),
                          "sample": s.desc + f"; one step = one pass over the sample with the fastest thread count ({best}); thread count from sched_getaffinity, OMP_NUM_THREADS ignored"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "GLIM's own CPU path (gtsam_points::IntegratedVGICPFactor) cannot be built here (GTSAM / gtsam_points / Eigen absent); this is the oracle port, fp64, all host threads",
