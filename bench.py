@@ -282,22 +282,27 @@ def reference_sample_global_mapping(scale, max_factors=16):
         if w.host_clouds[i] is None:
             w.host_clouds[i] = workloads.make_scan(sc, "os1_64", traj[i], synth.rng_for(401, i), n_rays=a["n_rays"], max_points=p.submap_target_num_points, ctx=None, use_gpu=False)
 
-    cur = n // 2 + n // 8
-    need(cur)
     picked = []
-    rng = synth.rng_for(402)
-    for i in range(cur):
-        if np.sum((traj[i][:3, 3] - traj[cur][:3, 3]) ** 2) > p.max_implicit_loop_distance**2:
-            continue
-        need(i)
-        gt = w.gt_delta(i, cur)
-        if w.overlap([i], len(w.resolutions) - 1, cur, [gt]) < p.min_implicit_loop_overlap:
-            continue
-        delta = synth.perturb(gt, rng, 0.02, 0.2)
-        for l in range(p.submap_voxelmap_levels):
-            picked.append((i, l, cur, delta))
-        if len(picked) >= max_factors:
+    # the fixed source submap of the full-size workload; a scaled-down (debug) layout may give it no partner: try later ones
+    for cur in [n // 2 + n // 8] + list(range(n - 1, 0, -1)):
+        need(cur)
+        rng = synth.rng_for(402)
+        for i in range(cur):
+            if np.sum((traj[i][:3, 3] - traj[cur][:3, 3]) ** 2) > p.max_implicit_loop_distance**2:
+                continue
+            need(i)
+            gt = w.gt_delta(i, cur)
+            if w.overlap([i], len(w.resolutions) - 1, cur, [gt]) < p.min_implicit_loop_overlap:
+                continue
+            delta = synth.perturb(gt, rng, 0.02, 0.2)
+            for l in range(p.submap_voxelmap_levels):
+                picked.append((i, l, cur, delta))
+            if len(picked) >= max_factors:
+                break
+        if picked:
             break
+    if not picked:
+        raise SystemExit("reference arm: the scaled layout has no overlapping submap pair (use a larger --scale)")
     s = CpuSample("global_mapping_gpu", w.resolutions, w.host_clouds, picked[:max_factors], f" (submap {cur}; its first {max_factors} factors in GlobalMapping::insert_submap order)")
     w.host_clouds = [c for c in w.host_clouds if c is not None]
     return s, w
@@ -319,7 +324,7 @@ def run_reference(args, rank):
         cfg = workload_config(args.workload, w, {"reference_step": s.desc})
     cfg["sample_build_seconds"] = round(time.perf_counter() - t_build, 1)
     cfg["same_config"] = "bounded sample: the factors of ONE source cloud of the workload (cache-friendly for the CPU), not the whole factor set"
-    best, per = cpu_thread_sweep(s, 10.0)  # pick the fastest thread count for this host, then time K steps with it
+    best, per = cpu_thread_sweep(s, min(10.0, args.cpu_seconds))  # pick the fastest thread count for this host, then time K steps with it
     for _ in range(max(1, min(args.warmup, 3))):
         s.run_once()
     # bound the run: at most ~60 s of CPU work
