@@ -571,9 +571,9 @@ def parity_check(env, w, fset, peers_row_fetch, K, seed=7):
 
 def run_preprocess(args, env):
     """--workload preprocess: one 60 k-point HDL-32e-shaped frame through the per-frame preprocess."""
-    from glim_b200 import preprocess_bench
+    import bench_preprocess
 
-    line = preprocess_bench.run(env, args, METRIC)
+    line = bench_preprocess.run(env, args, METRIC)
     if env.rank == 0:
         print(json.dumps(line))
 

@@ -1,6 +1,6 @@
 """bench.py --workload preprocess: the per-frame preprocess of north_star (voxel downsample + k-NN + covariance estimation, ending
-in the device cloud the VGICP factors read) on one HDL-32e-shaped 60 k-point frame, next to the CPU path.  Bench plumbing,
-not part of the drop-in surface."""
+in the device cloud the VGICP factors read) on one HDL-32e-shaped 60 k-point frame, next to the CPU path.  Bench plumbing next to
+bench.py (its cpu_baseline leg executes oracle/, which nothing under glim_b200/ may), not part of the drop-in surface."""
 import time
 
 import numpy as np

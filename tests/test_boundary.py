@@ -36,6 +36,25 @@ def test_library_is_sm100a_only_and_links_no_torch():
     assert "torch" not in ldd and "c10" not in ldd
 
 
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under glim_b200/ or include/ may import, include or link it, and the library must
+    not depend on libglim_oracle.so (only tests/, __graft_entry__.smoke() and bench.py's checker / CPU legs may use it)."""
+    offenders = []
+    for base in ("glim_b200", "include"):
+        for d, _, files in os.walk(os.path.join(ROOT, base)):
+            if "build" in d.split(os.sep) or "__pycache__" in d:
+                continue
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", "Makefile")):
+                    continue
+                txt = open(os.path.join(d, f), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|#include\s*[<\"][^>\"]*oracle|libglim_oracle|-lglim_oracle|dlopen[^\n]*oracle", txt, flags=re.M):
+                    offenders.append(os.path.join(d, f))
+    assert not offenders, offenders
+    needed = os.popen(f"readelf -d {capi.SO_PATH}").read()
+    assert "NEEDED" in needed and "oracle" not in needed
+
+
 def test_status_strings():
     L = capi.lib()
     assert L.gb_status_string(0) == b"ok"
