@@ -1,11 +1,16 @@
 """Sharding of a global-mapping relinearization sweep across the GPUs of one box.
 
 The reference has no multi-GPU notion; this is the B200-native addition north_star asks for.
-Every rank holds all submap clouds and voxel maps (replicated at insert time, < 1 GB); the (target, source) PAIRS of
-the factor graph are partitioned over the ranks (both voxel levels of a pair stay together, longest-processing-time
-first on the source size); each rank sweeps its factors with the fused kernel, whose epilogue adds every factor's
-blocks into its pair's row of a zeroed fp32 slab [num_pairs][GB_SLAB_STRIDE]; one all-reduce (sum) of the slab over
-NCCL / NVLink gives every rank the complete block-sparse Hessian for the host solver.
+Every rank holds all submap clouds and voxel maps (replicated at insert time, ~1.5 GB); the (target, source) PAIRS of the
+factor graph are partitioned over the ranks -- both voxel levels of a pair stay together; by default `world` CONTIGUOUS chunks
+of the reference's source-major factor order, cut at equal cost (measured inliers, then per-rank kernel-time feedback), so that
+a rank keeps all factors of the source clouds it touches.  Each rank sweeps its factors with the fused kernel.  Result exchange,
+two variants:
+  * peer slab (default, `gpu.PeerSlab`): every pair is owned by one rank, whose kernel stores the finished fp32 row
+    [GB_SLAB_STRIDE] into every rank's IPC-mapped slab over NVLink -- an all-gather done by the producers, no NCCL in the step;
+  * local slab + one NCCL all-reduce (sum) of [num_pairs][GB_SLAB_STRIDE] (`ShardedSweep` below; `bench.py --collective nccl`,
+    and the world-size-2 gloo test on the CPU-only box).
+Either way every rank ends up with the complete block-sparse Hessian for its copy of the host solver.
 """
 from __future__ import annotations
 
