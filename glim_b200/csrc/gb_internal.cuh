@@ -158,7 +158,7 @@ struct gb_sweep {
   PeerPush* d_peer_tables;        // [2]: one per step parity
   std::vector<int> h_pair;        // pair id per factor
   int num_tiles, tile_size, grid;   // work items, points per item, CTAs
-  int kernel_version;               // 5 = default kernel; 4 = bulk-async (TMA) staged kernel; 3 = round-1 kernel (GB_KERNEL=3/4)
+  int kernel_version;               // 5 = small sweeps (one wave of strided items); 3 = large sweeps (queue of contiguous items); 4 = bulk-async (TMA) staged experiment (GB_KERNEL=3/4/5 forces one)
   bool any_sv;                      // some factor of the sweep has surface validation on
   int pipe;                         // v5 software-pipelining variant (GB_PIPE; A/B only)
   int strided;                      // v5, about one item per warp: item j of a factor owns the rows j, j + J, ... (see k_vgicp_sweep5)

@@ -68,9 +68,10 @@ typedef struct gb_linearized6 {
 
 /* factor flags */
 #define GB_FACTOR_DEFAULT 0
-/* set_enable_surface_validation(true) (odometry_estimation_gpu.cpp:145,162).  The reference rule is
- * not recoverable here (unpinned ledger); the flag is accepted and recorded, the
- * documented rule is in DESIGN.md. */
+/* set_enable_surface_validation(true) (odometry_estimation_gpu.cpp:145,162).  The reference rule lives in the
+ * un-vendored gtsam_points and is not recoverable here (unpinned ledger); implemented is the documented
+ * orientation-consistency gate of DESIGN.md section 7: with n = R n_source, a correspondence is kept iff
+ * 3 n^T C_voxel n <= tr(C_voxel).  The source cloud must carry normals (gb_vgicp_factor_create fails otherwise). */
 #define GB_FACTOR_SURFACE_VALIDATION 1
 
 GB_API const char* gb_status_string(gb_status s);
