@@ -23,6 +23,19 @@ def test_header_is_plain_c(tmp_path):
     assert subprocess.call([str(exe)]) == 0
 
 
+def test_plain_c_consumer_dlopens_the_library_and_resolves_every_entry_point(tmp_path):
+    """SURVEY section 4, boundary tier: a C99 program (what a cgo / JNI stub would be) dlopen()s libglim_b200.so, resolves every
+    symbol the header declares and drives the device-free part of the protocol; without a device gb_ctx_create must fail with
+    GB_ERR_NO_DEVICE (no CPU fallback), with one it must succeed.  Runs on both boxes."""
+    from glim_b200 import capi
+
+    exe = tmp_path / "cabi_smoke"
+    subprocess.check_call([GCC, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{INC}", os.path.join(CPP, "cabi_smoke.c"), "-o", str(exe), "-ldl"])
+    r = subprocess.run([str(exe), capi.SO_PATH, *capi.SYMBOLS], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert f"{len(capi.SYMBOLS)} symbols" in r.stdout
+
+
 def test_shims_compile_standalone_and_gtsam_mode(tmp_path):
     subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{INC}", "-c", os.path.join(CPP, "shim_main.cpp"), "-o", str(tmp_path / "a.o")])
     subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{INC}", f"-I{os.path.join(CPP, 'gtsam_stub')}", "-c", os.path.join(CPP, "gtsam_mode_check.cpp"), "-o", str(tmp_path / "b.o")])

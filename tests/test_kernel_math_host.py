@@ -214,3 +214,39 @@ def test_coord_hash_and_slab_map(km):
     idx = [km.km_slab_to_record(e) for e in range(92)]
     assert len(set(idx)) == 92
     assert np.array_equal(np.asarray(row[:92], dtype=np.float64), flat[idx])
+
+
+def test_adversarial_and_generated_poses(km, data):
+    """SURVEY section 4 'kernel parity' tier on the CPU-only box: identity, 180 degree yaw, large translations (negative
+    coordinates, hash wrap), no overlap at all -- then hypothesis-generated poses.  Inlier sets must be exact for every pose
+    (the lookup is integer work on explicitly fused fp32 arithmetic), Hessians within the 1e-4 bar wherever there are inliers."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    sp, packed, T_gt = data
+    m = oracle.GpuMap(*packed[0], 0.5)
+    xyz, cov6 = packed[1]
+
+    def check(T):
+        acc, corr = sweep(km, m, xyz, cov6, T)
+        ref_raw, ref_corr = oracle.linearize_gpumap(m, xyz, cov6, T)
+        ref = oracle.split122(ref_raw)
+        assert np.array_equal(corr, ref_corr)
+        H, b, e, n = unpack29(acc)
+        assert n == ref["num_inliers"]
+        if n >= 50:  # a handful of inliers is a cancelling sum of a few terms: the bar is stated for a registration-sized set
+            assert rel_err(H, ref["H_tt"]) < REL_TOL
+            assert abs(e - ref["error"]) < REL_TOL * max(ref["error"], 1e-12)
+        return n
+
+    assert check(np.eye(4)) > 0
+    for T in (synth.pose(0, 0, 0, np.pi), synth.pose(3.0, -2.0, 0.1, 0.3, 0.02, -0.01), synth.pose(-7.5, 4.25, 0.0, -2.0)):
+        check(T)
+    assert check(synth.pose(5000.0, -3000.0, 100.0, 1.0)) == 0
+    assert check(synth.pose(-40000.0, 65000.0, -300.0, -0.7)) == 0  # |voxel coordinate| ~ 1.3e5: the u32 hash wraps
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.floats(-np.pi, np.pi), st.floats(-0.3, 0.3), st.floats(-0.3, 0.3), st.floats(-8, 8), st.floats(-8, 8), st.floats(-1, 1))
+    def generated(yaw, pitch, roll, x, y, z):
+        check(T_gt @ synth.pose(x, y, z, yaw, pitch, roll))
+
+    generated()
