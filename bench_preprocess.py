@@ -29,6 +29,7 @@ def run(env, args, metric_name):
     from glim_b200 import preprocess, synth
 
     torch = env.torch
+    sampler = bench.ClockSampler(env.local_rank) if env.rank == 0 else None  # nvidia-smi clocks / throttle reasons during the timed region
     sc = synth.make_hall_scene()
     pts, tms = synth.scan(sc, "hdl32", synth.arc_trajectory(8)[2], synth.rng_for(32))
     n = len(pts)
@@ -51,7 +52,12 @@ def run(env, args, metric_name):
     launches = env.ctx.kernel_launches - l0
     for _ in range(3):
         step_e2e()
-    ems, _, _, _ = env.timed(step_e2e, steps, False)
+    ems, _, _, t1e = env.timed(step_e2e, steps, False)
+    clocks = None
+    if sampler:
+        time.sleep(0.15)
+        sampler.stop()
+        clocks = sampler.summary(t0, t1e)
     fr, normals, covs, cloud = step_e2e()
     m = fr.size()
     # parity spot check against the CPU pipeline (indices exact, covariances 1e-9)
@@ -80,7 +86,7 @@ def run(env, args, metric_name):
         "config": {"workload": "preprocess", "raw_points": n, "frame_points": int(m), "sensor": "HDL-32e-shaped, 60 000 rays", "downsample_resolution_m": 0.1, "k_correspondences": 10,
                    "note": "value: raw scan H2D from pinned memory + all stages on the device, result = the device cloud (no host products); e2e: the same + PreprocessedFrame fields, fp64 covariances and normals copied back"},
         "e2e": {"value": n / (ems / steps * 1e-3) / 1e6, "unit": "M raw points/s", "ms_per_step": ems / steps, "h2d_bytes_per_step": int(n * 40), "d2h_bytes_per_step": int(m * (32 + 8 + 4 * params.k_correspondences + 128 + 32))},
-        "gpu_launches": int(launches), "clocks": None,
+        "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": alg / (per * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (per * 1e-3) / 1e9 / peak, "traffic": None,
                      "note": "a 60 k-point frame is ~20 short launches (sorts, scans, hash build, k-NN, covariances, reorder): launch- and latency-bound, far from the HBM roofline by construction"},
         "cpu_baseline": {"value": n / (cpu_ms * 1e-3) / 1e6, "unit": "M raw points/s", "ms_per_frame": cpu_ms, "cores": threads, "kind": "port", "ms_by_threads": {str(t): round(1e3 * v, 2) for t, v in t_cpu.items()},
