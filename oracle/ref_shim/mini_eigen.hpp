@@ -14,14 +14,24 @@
 #include <limits>
 #include <vector>
 
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
 namespace Eigen {
 
 template <int R, int C> struct Mat;
 
 template <int N> struct DiagWrap { double d[N]; };
+template <int N> struct BoolArray {
+  bool b[N];
+  bool any() const { for (int k = 0; k < N; k++) if (b[k]) return true; return false; }
+  bool all() const { for (int k = 0; k < N; k++) if (!b[k]) return false; return true; }
+};
 template <int N> struct ArrayWrap {
   double v[N];
   Mat<N, 1> max(double m) const;
+  BoolArray<N> operator>(const ArrayWrap& o) const { BoolArray<N> r; for (int k = 0; k < N; k++) r.b[k] = v[k] > o.v[k]; return r; }
+  BoolArray<N> operator>=(const ArrayWrap& o) const { BoolArray<N> r; for (int k = 0; k < N; k++) r.b[k] = v[k] >= o.v[k]; return r; }
+  BoolArray<N> operator<=(const ArrayWrap& o) const { BoolArray<N> r; for (int k = 0; k < N; k++) r.b[k] = v[k] <= o.v[k]; return r; }
 };
 
 // lvalue block of a matrix (c.block<3,3>(0,0) = ..., T.translation() = ..., T.linear() = ...)
@@ -46,6 +56,11 @@ template <int R, int C> struct Mat {
   Mat(double x, double y, double z) { static_assert(R * C == 3, "3-vector"); a[0] = x; a[1] = y; a[2] = z; }
   template <int RR, int CC> Mat(const BlockRef<R, C, RR, CC>& b) { *this = (Mat<R, C>)b; }
 
+  void setZero() { for (int k = 0; k < R * C; k++) a[k] = 0.0; }
+  bool allFinite() const { for (int k = 0; k < R * C; k++) if (!std::isfinite(a[k])) return false; return true; }
+  double* data() { return a; }
+  const double* data() const { return a; }
+  template <int K> Mat<K, 1> head() const { static_assert(C == 1 && K <= R, "vector"); Mat<K, 1> h; for (int k = 0; k < K; k++) h.a[k] = a[k]; return h; }
   static Mat Zero() { Mat m; for (int k = 0; k < R * C; k++) m.a[k] = 0.0; return m; }
   static Mat Identity() { Mat m = Zero(); for (int k = 0; k < (R < C ? R : C); k++) m(k, k) = 1.0; return m; }
 
@@ -287,6 +302,7 @@ public:
     r.translation() = linear() * o.translation() + translation();
     return r;
   }
+  Vector3d operator*(const Vector3d& p) const { return linear() * p + translation(); }  // R p + t
   Vector4d operator*(const Vector4d& v) const {  // (3x4 affine part) * v, last coefficient copied
     Vector4d r;
     for (int i = 0; i < 3; i++) {

@@ -132,3 +132,115 @@ def test_product_host_pose_table_equals_reference_translation_unit(ref):
     assert np.abs(np.einsum("nij,nj->ni", Ts[idx], pts) - ref_deskew_cv(ref, T_IL, V, W, times, pts)).max() < 1e-11
     idx, Ts = preprocess.deskew_pose_table(T_IL, times, imu_times=IMU_T, imu_poses=IMU_P, stamp=100.0)
     assert np.abs(np.einsum("nij,nj->ni", Ts[idx], pts) - ref_deskew_imu(ref, T_IL, IMU_T, IMU_P, 100.0, times, pts)).max() < 1e-11
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# CloudPreprocessor::preprocess: the reference's cloud_preprocessor.cpp, compiled unmodified.  Its gtsam_points leaf calls
+# (voxelgrid_sampling, randomgrid_sampling, sample, filter, remove_outliers, KdTree) are [EXT] and resolve to stand-ins that forward to
+# the oracle's leaves -- so what this checks is the reference file's OWN logic against the composition the GPU parity tests use as
+# their oracle (`_cpu_frame` in tests/test_gpu_parity.py): which stage runs when, the finite / range gates, the sort key, global
+# shutter, the crop box in either frame, where outlier removal sits, scan_end_time, the k-NN layout and its self-fill.
+# ------------------------------------------------------------------------------------------------------------------------
+class RefParams(C.Structure):
+    _fields_ = [("distance_near_thresh", C.c_double), ("distance_far_thresh", C.c_double), ("use_random_grid_downsampling", C.c_int), ("downsample_resolution", C.c_double),
+                ("downsample_target", C.c_int), ("downsample_rate", C.c_double), ("seed", C.c_ulonglong), ("global_shutter", C.c_int), ("crop_bbox_frame", C.c_int),
+                ("crop_bbox_min", C.c_double * 3), ("crop_bbox_max", C.c_double * 3), ("T_imu_lidar", C.c_double * 16), ("enable_outlier_removal", C.c_int),
+                ("outlier_removal_k", C.c_int), ("outlier_std_mul_factor", C.c_double), ("k_correspondences", C.c_int), ("num_threads", C.c_int)]
+
+
+def ref_preprocess(L, P, T, stamp=10.0, intensities=None, **kw):
+    par = RefParams(distance_near_thresh=1.0, distance_far_thresh=60.0, use_random_grid_downsampling=0, downsample_resolution=0.2, downsample_target=0, downsample_rate=0.3,
+                    seed=5, global_shutter=0, crop_bbox_frame=0, enable_outlier_removal=0, outlier_removal_k=10, outlier_std_mul_factor=1.0, k_correspondences=10, num_threads=2)
+    par.T_imu_lidar = (C.c_double * 16)(*oracle.pose_colmajor(np.eye(4)))
+    for k, v in kw.items():
+        if k in ("crop_bbox_min", "crop_bbox_max"):
+            v = (C.c_double * 3)(*v)
+        elif k == "T_imu_lidar":
+            v = (C.c_double * 16)(*oracle.pose_colmajor(v))
+        setattr(par, k, v)
+    n = len(P)
+    P, T = np.ascontiguousarray(P, np.float64), np.ascontiguousarray(T, np.float64)
+    op, ot, oi, nb = np.zeros((n, 4)), np.zeros(n), np.zeros(n), np.zeros((n, par.k_correspondences), np.int32)
+    end, seen = C.c_double(), (C.c_double * 6)()
+    L.ref_preprocess.restype = C.c_int
+    L.ref_preprocess.argtypes = [C.c_void_p, C.c_double, C.c_int] + [C.c_void_p] * 9
+    it = np.ascontiguousarray(intensities, np.float64) if intensities is not None else None
+    m = L.ref_preprocess(C.byref(par), stamp, n, _p(P), _p(T), _p(it) if it is not None else None, _p(op), _p(ot), _p(oi), _p(nb), C.byref(end), seen)
+    return op[:m], ot[:m], oi[:m], nb[:m], end.value, list(seen)
+
+
+@pytest.fixture(scope="module")
+def frame():
+    sc = synth.make_hall_scene()
+    P, T = synth.scan(sc, "hdl32", synth.arc_trajectory(8)[2], synth.rng_for(41), n_rays=32 * 250)
+    P = P.copy()
+    P[17, 1] = np.nan  # dropped by the finite gate (cloud_preprocessor.cpp:123)
+    return P, T
+
+
+def canonical(pts, tms, nb, extra=None):
+    """The reference orders by time with std::sort (NOT stable: the order of equal times is unspecified, SURVEY C.1) and the 32
+    rings of a firing share a timestamp, so frames are compared modulo the order inside a group of equal times: rows sorted by
+    (time, x, y, z), neighbour indices renumbered accordingly, every neighbour row as a sorted set."""
+    perm = np.lexsort((pts[:, 2], pts[:, 1], pts[:, 0], tms))
+    inv = np.empty(len(perm), np.int64)
+    inv[perm] = np.arange(len(perm))
+    out = [pts[perm], tms[perm], np.sort(inv[nb[perm]], axis=1)]
+    if extra is not None:
+        out.append(extra[perm])
+    return out
+
+
+def test_preprocess_composition_equals_reference_translation_unit(ref, frame):
+    from tests.test_gpu_parity import _cpu_frame
+
+    P, T = frame
+    lo, hi = np.array([-3.0, -2.0, -5.0]), np.array([4.0, 2.5, 5.0])
+    cases = {
+        "voxelgrid": (dict(), dict()),
+        "cropbox lidar": (dict(crop_bbox_frame=1, crop_bbox_min=lo, crop_bbox_max=hi), dict(crop=(lo, hi))),
+        "outliers": (dict(enable_outlier_removal=1, outlier_removal_k=8, outlier_std_mul_factor=1.0), dict(sor=(8, 1.0))),
+    }
+    for name, (rkw, okw) in cases.items():
+        pts, tms, _, nb, end, seen = ref_preprocess(ref, P, T, **rkw)
+        o_pts, o_tms, o_nb, _, _ = _cpu_frame(P, T, 0.2, 1.0, 60.0, 10, **okw)
+        assert len(pts) == len(o_pts) > 1000, name
+        assert np.array_equal(tms, o_tms), name  # the sequence of times is order-free
+        for a, b in zip(canonical(pts, tms, nb), canonical(o_pts, o_tms, o_nb)):
+            assert np.array_equal(a, b), name
+        assert end == 10.0 + o_tms[-1], name
+    # the code defaults of CloudPreprocessorParams (cloud_preprocessor.cpp:27-36,58) as the product's gb_preprocess_default_params
+    # documents them next to the shipped config
+    assert seen == [1.0, 100.0, 0.15, 0.3, 2.0, 8.0]
+    # random grid: rate = target / N (cloud_preprocessor.cpp:105), survivors keep their order, then the same gates
+    target = 2000
+    pts, tms, _, nb, _, _ = ref_preprocess(ref, P, T, use_random_grid_downsampling=1, downsample_resolution=1.0, downsample_target=target, seed=5)
+    mask = oracle.randomgrid_sampling(P, 1.0, target / len(P), seed=5)
+    o_pts, o_tms, o_nb, _, _ = _cpu_frame(P, T, None, 1.0, 60.0, 10, mask=mask)
+    assert len(pts) == len(o_pts) > 500
+    for a, b in zip(canonical(pts, tms, nb), canonical(o_pts, o_tms, o_nb)):
+        assert np.array_equal(a, b)
+
+
+def test_preprocess_global_shutter_intensities_and_imu_crop_box(ref, frame):
+    P, T = frame
+    inten = np.linspace(0.0, 1.0, len(P))
+    pts, tms, it, nb, end, _ = ref_preprocess(ref, P, T, intensities=inten, global_shutter=1)
+    # global shutter: the points are still ordered by their ORIGINAL times, then every time becomes 0 (:135-140) -> scan_end_time = stamp
+    o_pts, o_tms, o_it = oracle.voxelgrid_sampling(P, 0.2, times=T, intensities=inten)
+    sq = (o_pts[:, :3] ** 2).sum(1)
+    keep = np.nonzero((sq > 1.0) & (sq < 3600.0) & np.isfinite(o_pts).all(1))[0]
+    keep = keep[np.argsort(o_tms[keep], kind="stable")]
+    assert np.all(tms == 0.0) and end == 10.0
+    zero_nb = np.zeros((len(pts), 1), np.int64)
+    got, want = canonical(pts, o_tms[keep], zero_nb, it), canonical(o_pts[keep], o_tms[keep], zero_nb, o_it[keep])
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[3], want[3])  # intensities travel with the points
+    # crop box given in the IMU frame: p_imu = T_imu_lidar * p_lidar (:152-157); points INSIDE the box are removed
+    T_il = synth.pose(0.5, -0.2, 0.1, 0.4, 0.0, 0.0)
+    lo, hi = np.array([-3.0, -2.0, -5.0]), np.array([4.0, 2.5, 5.0])
+    pts2, _, _, _, _, _ = ref_preprocess(ref, P, T, crop_bbox_frame=2, crop_bbox_min=lo, crop_bbox_max=hi, T_imu_lidar=T_il)
+    base = o_pts[keep]
+    p_imu = base[:, :3] @ T_il[:3, :3].T + T_il[:3, 3]
+    inside = (p_imu >= lo).all(1) & (p_imu <= hi).all(1)
+    assert 0 < inside.sum() < len(base)
+    assert np.array_equal(pts2[np.lexsort(pts2[:, :3].T)], base[~inside][np.lexsort(base[~inside][:, :3].T)])
