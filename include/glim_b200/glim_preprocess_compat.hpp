@@ -6,6 +6,8 @@
 //   glim::PreprocessedFrame / glim::RawPoints        include/glim/preprocess/preprocessed_frame.hpp:14-38
 //   glim::CloudCovarianceEstimation::estimate         include/glim/common/cloud_covariance_estimation.hpp:17-60,
 //        src/glim/common/cloud_covariance_estimation.cpp:24-122  (called at src/glim/odometry/odometry_estimation_imu.cpp:322-328)
+//   glim::CloudDeskewing::deskew (both overloads)     include/glim/common/cloud_deskewing.hpp:11-50, src/glim/common/cloud_deskewing.cpp:11-133
+//        (called at src/glim/odometry/odometry_estimation_imu.cpp:313, src/glim/mapping/sub_mapping.cpp:365)
 //
 // Same member names and call signatures; Eigen::Vector4d / Matrix4d are the layout-compatible PODs of
 // gtsam_points_compat.hpp (real Eigen types with -DGLIM_B200_WITH_GTSAM).  Namespace `glim_b200::glim` so that the header can
@@ -176,6 +178,76 @@ public:
   }
 
 private:
+  CUstream_st* stream_;
+};
+
+/// Layout-compatible stand-in for Eigen::Vector3d (24 B); the real type with -DGLIM_B200_WITH_GTSAM
+#if defined(GLIM_B200_WITH_GTSAM) && defined(EIGEN_WORLD_VERSION)
+using Vector3d = Eigen::Vector3d;
+#else
+struct Vector3d {
+  double v[3] = {0.0, 0.0, 0.0};
+  Vector3d() = default;
+  Vector3d(double x, double y, double z) : v{x, y, z} {}
+  static Vector3d Zero() { return Vector3d(); }
+  double& operator[](int i) { return v[i]; }
+  double operator[](int i) const { return v[i]; }
+  const double* data() const { return v; }
+};
+#endif
+static_assert(sizeof(Pose) == 16 * sizeof(double), "std::vector<Pose> is a dense array of column-major 4x4 matrices");
+
+/// glim::CloudDeskewing: same two overloads, same argument order.  The per-point transform runs on the device (gb_deskew); the
+/// time table and the pose per 0.1 ms slot are built on the host, as the reference does (cloud_deskewing.cpp:22-43, :75-121).
+class CloudDeskewing {
+public:
+  explicit CloudDeskewing(CUstream_st* stream = nullptr) : stream_(stream) {}
+  ~CloudDeskewing() = default;
+
+  /// constant linear / angular velocity (cloud_deskewing.cpp:11-55)
+  std::vector<Vector4d> deskew(const Pose& T_imu_lidar, const Vector3d& linear_vel, const Vector3d& angular_vel, const std::vector<double>& times, const std::vector<Vector4d>& points) {
+    return run(T_imu_lidar, linear_vel.data(), angular_vel.data(), nullptr, nullptr, 0.0, times, points, nullptr);
+  }
+  /// predicted IMU poses (cloud_deskewing.cpp:57-133); no poses -> the zero-velocity model (:69-71)
+  std::vector<Vector4d> deskew(const Pose& T_imu_lidar, const std::vector<double>& imu_times, const std::vector<Pose>& imu_poses, const double stamp, const std::vector<double>& times,
+                               const std::vector<Vector4d>& points) {
+    return run(T_imu_lidar, nullptr, nullptr, &imu_times, &imu_poses, stamp, times, points, nullptr);
+  }
+  /// extension: the `pt = T_imu_lidar * pt` loop that follows the call (odometry_estimation_imu.cpp:314-316) fused into the kernel
+  std::vector<Vector4d> deskew_and_transform(const Pose& T_imu_lidar, const std::vector<double>& imu_times, const std::vector<Pose>& imu_poses, const double stamp, const std::vector<double>& times,
+                                             const std::vector<Vector4d>& points, const Pose& T_post) {
+    return run(T_imu_lidar, nullptr, nullptr, &imu_times, &imu_poses, stamp, times, points, &T_post);
+  }
+
+  /// The host half on its own (no device needed): slot index per point and T_lidar0_lidar1 per slot -- what deskew() hands to the
+  /// kernel.  velocities / imu arguments as in the two overloads (pass nullptr for the half that is not used).
+  static void pose_table(const Pose& T_imu_lidar, const Vector3d* linear_vel, const Vector3d* angular_vel, const std::vector<double>* imu_times, const std::vector<Pose>* imu_poses, const double stamp,
+                         const std::vector<double>& times, std::vector<int>& time_indices, std::vector<Pose>& T_lidar0_lidar1) {
+    const std::size_t n = times.size();
+    time_indices.assign(n, 0);
+    T_lidar0_lidar1.assign(n, Pose());
+    std::size_t slots = 0;
+    const std::size_t n_imu = (imu_times && imu_poses) ? imu_poses->size() : 0;
+    if (imu_times && imu_poses && imu_times->size() != imu_poses->size()) throw std::runtime_error("imu_times.size() != imu_poses.size()");
+    check(gb_deskew_pose_table(T_imu_lidar.data(), linear_vel ? linear_vel->data() : nullptr, angular_vel ? angular_vel->data() : nullptr, n_imu, n_imu ? imu_times->data() : nullptr,
+                               n_imu ? (*imu_poses)[0].data() : nullptr, stamp, n, times.data(), time_indices.data(), n ? const_cast<double*>(T_lidar0_lidar1[0].data()) : nullptr, &slots),
+          "gb_deskew_pose_table");
+    T_lidar0_lidar1.resize(slots);
+  }
+
+private:
+  std::vector<Vector4d> run(const Pose& T_imu_lidar, const double* linear_vel, const double* angular_vel, const std::vector<double>* imu_times, const std::vector<Pose>* imu_poses, const double stamp,
+                            const std::vector<double>& times, const std::vector<Vector4d>& points, const Pose* T_post) {
+    if (times.empty()) return std::vector<Vector4d>();  // cloud_deskewing.cpp:17-19, :65-67
+    if (times.size() != points.size()) throw std::runtime_error("times.size() != points.size()");
+    const std::size_t n_imu = (imu_times && imu_poses) ? imu_poses->size() : 0;
+    if (imu_times && imu_poses && imu_times->size() != imu_poses->size()) throw std::runtime_error("imu_times.size() != imu_poses.size()");
+    std::vector<Vector4d> out(points.size());
+    check(gb_deskew(Context::of_stream(stream_), T_imu_lidar.data(), linear_vel, angular_vel, n_imu, n_imu ? imu_times->data() : nullptr, n_imu ? (*imu_poses)[0].data() : nullptr, stamp, points.size(),
+                    times.data(), reinterpret_cast<const double*>(points.data()), T_post ? T_post->data() : nullptr, reinterpret_cast<double*>(out.data())),
+          "gb_deskew");
+    return out;
+  }
   CUstream_st* stream_;
 };
 

@@ -43,6 +43,62 @@ def test_shims_compile_standalone_and_gtsam_mode(tmp_path):
     subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{INC}", "-c", os.path.join(CPP, "preprocess_main.cpp"), "-o", str(tmp_path / "d.o")])
 
 
+def test_shim_api_matches_the_reference_headers(tmp_path):
+    """The reference's own cloud_preprocessor.hpp / cloud_covariance_estimation.hpp / cloud_deskewing.hpp (compiled against the Eigen
+    stand-in of oracle/ref_shim) and the shims in one translation unit: call-site templates instantiated with both must compile."""
+    ref_inc = "/root/reference/include"
+    if not os.path.isdir(ref_inc):
+        pytest.skip("/root/reference is not present on this box")
+    subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-Wno-sign-compare", f"-I{os.path.join(ROOT, 'oracle', 'ref_shim')}", f"-I{ref_inc}", f"-I{INC}",
+                           "-c", os.path.join(CPP, "api_conformance.cpp"), "-o", str(tmp_path / "api.o")])
+
+
+def test_cloud_deskewing_shim_host_half_matches_oracle_and_reference(tmp_path):
+    """glim::CloudDeskewing shim (glim_preprocess_compat.hpp): its host half -- time table + pose per slot, the arguments exactly as
+    deskew() marshals them -- built against the library and RUN on this box; applied on the host it must reproduce the oracle and,
+    where oracle/_ref is built, the reference's own cloud_deskewing.cpp.  Without a device deskew() itself must throw."""
+    import ctypes as C
+    import struct
+
+    from oracle import oracle
+    from tests.test_deskew import IMU_P, IMU_T, T_IL, V, W, scan_like
+
+    lib_dir = os.path.join(ROOT, "glim_b200")
+    exe = tmp_path / "deskew_host"
+    subprocess.check_call([GXX, "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", f"-I{INC}", os.path.join(CPP, "deskew_host_main.cpp"), "-o", str(exe),
+                           f"-L{lib_dir}", "-lglim_b200", f"-Wl,-rpath,{lib_dir}"])
+    times, pts = scan_like(n=5000, seed=7)
+    n = len(pts)
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    poses = np.ascontiguousarray(np.swapaxes(IMU_P, 1, 2)).reshape(-1, 16)
+    with open(inp, "wb") as f:
+        f.write(struct.pack("i", n) + times.tobytes() + np.ascontiguousarray(pts).tobytes() + oracle.pose_colmajor(T_IL).tobytes() + V.tobytes() + W.tobytes())
+        f.write(struct.pack("i", len(IMU_T)) + np.ascontiguousarray(IMU_T).tobytes() + poses.tobytes() + struct.pack("d", 100.0))
+    r = subprocess.run([str(exe), str(inp), str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    raw = open(out, "rb").read()
+    a = np.frombuffer(raw, np.float64, 4 * n).reshape(n, 4)
+    b = np.frombuffer(raw, np.float64, 4 * n, offset=32 * n).reshape(n, 4)
+    slots, threw = struct.unpack("ii", raw[64 * n:])
+    assert slots > 100
+    assert np.abs(a - oracle.deskew_const_vel(T_IL, V, W, times, pts)).max() < 1e-11
+    assert np.abs(b - oracle.deskew_imu(T_IL, IMU_T, IMU_P, 100.0, times, pts)).max() < 1e-11
+    from glim_b200 import capi
+
+    if capi.lib().gb_device_count() == 0:
+        assert threw == 1, "deskew() must fail loudly without a device (no CPU fallback)"
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libglim_ref.so")
+    if os.path.exists(ref_so):
+        from tests.test_oracle_vs_reference_tu import ref_deskew_cv, ref_deskew_imu
+
+        L = C.CDLL(ref_so)
+        vp, i32 = C.c_void_p, C.c_int
+        L.ref_deskew_const_vel.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+        L.ref_deskew_imu.argtypes = [vp, i32, vp, vp, C.c_double, i32, vp, vp, vp]
+        assert np.abs(a - ref_deskew_cv(L, T_IL, V, W, times, pts)).max() < 1e-11
+        assert np.abs(b - ref_deskew_imu(L, T_IL, IMU_T, IMU_P, 100.0, times, pts)).max() < 1e-11
+
+
 def test_host_side_helpers_run_without_a_device(tmp_path):
     """random_sampling / sample (sub_mapping.cpp:385, global_mapping.cpp:248), the factor-set hook (offline_viewer.cpp:29) and
     VoxelBucket: host code of the shim, built against the library and run here (no device call is made)."""
