@@ -213,6 +213,12 @@ public:
                                const std::vector<Vector4d>& points) {
     return run(T_imu_lidar, nullptr, nullptr, &imu_times, &imu_poses, stamp, times, points, nullptr);
   }
+  /// the same with the container GLIM passes: std::vector<Eigen::Isometry3d> pred_imu_poses (odometry_estimation_imu.cpp:313)
+  template <class Iso, class Alloc, class = std::enable_if_t<!std::is_same<Iso, Pose>::value && std::is_constructible<Pose, const Iso&>::value>>
+  std::vector<Vector4d> deskew(const Pose& T_imu_lidar, const std::vector<double>& imu_times, const std::vector<Iso, Alloc>& imu_poses, const double stamp, const std::vector<double>& times,
+                               const std::vector<Vector4d>& points) {
+    return deskew(T_imu_lidar, imu_times, std::vector<Pose>(imu_poses.begin(), imu_poses.end()), stamp, times, points);
+  }
   /// extension: the `pt = T_imu_lidar * pt` loop that follows the call (odometry_estimation_imu.cpp:314-316) fused into the kernel
   std::vector<Vector4d> deskew_and_transform(const Pose& T_imu_lidar, const std::vector<double>& imu_times, const std::vector<Pose>& imu_poses, const double stamp, const std::vector<double>& times,
                                              const std::vector<Vector4d>& points, const Pose& T_post) {

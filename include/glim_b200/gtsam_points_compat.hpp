@@ -49,6 +49,7 @@
 #include <functional>
 #include <string>
 #include <stdexcept>
+#include <type_traits>
 #include <string>
 #include <utility>
 #include <vector>
@@ -114,6 +115,14 @@ static_assert(sizeof(Vector4d) == 32 && sizeof(Matrix4d) == 128, "host element l
 /// 4x4 rigid transform, 16 doubles column-major (bit-compatible with Eigen::Isometry3d::data()).
 struct Pose {
   std::array<double, 16> m{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}};
+  Pose() = default;
+  /// From Eigen::Isometry3d (what GLIM's call sites pass: `T_a.inverse() * T_b`, odometry_estimation_gpu.cpp:228, :247, :265;
+  /// sub_mapping.cpp:253; global_mapping.cpp:320) or any transform whose .matrix() exposes 16 column-major doubles.
+  template <class Iso, class = decltype(static_cast<const double*>(std::declval<const Iso&>().matrix().data()))>
+  Pose(const Iso& iso) {
+    const auto& M = iso.matrix();
+    for (int e = 0; e < 16; e++) m[static_cast<std::size_t>(e)] = M.data()[e];
+  }
   const double* data() const { return m.data(); }
   double& operator()(int r, int c) { return m[c * 4 + r]; }
   double operator()(int r, int c) const { return m[c * 4 + r]; }
@@ -418,6 +427,15 @@ inline PointCloud::Ptr merge_frames(const std::vector<glim_b200::Pose>& poses, c
   for (const auto& f : frames)
     if (!std::dynamic_pointer_cast<const PointCloudGPU>(f)) throw std::runtime_error("merge_frames: frames must be PointCloudGPU (clone them first); libglim_b200 has no CPU path");
   return merge_frames_gpu(poses, frames, downsample_resolution, target_num_points);
+}
+/// the same with the container GLIM passes: std::vector<Eigen::Isometry3d> poses_to_merge (sub_mapping.cpp:486-496)
+template <class Iso, class Alloc, class = std::enable_if_t<!std::is_same<Iso, glim_b200::Pose>::value && std::is_constructible<glim_b200::Pose, const Iso&>::value>>
+inline PointCloudGPU::Ptr merge_frames_gpu(const std::vector<Iso, Alloc>& poses, const std::vector<PointCloud::ConstPtr>& frames, double downsample_resolution, int target_num_points = 0, CUstream_st* stream = nullptr, std::uint64_t seed = 0) {
+  return merge_frames_gpu(std::vector<glim_b200::Pose>(poses.begin(), poses.end()), frames, downsample_resolution, target_num_points, stream, seed);
+}
+template <class Iso, class Alloc, class = std::enable_if_t<!std::is_same<Iso, glim_b200::Pose>::value && std::is_constructible<glim_b200::Pose, const Iso&>::value>>
+inline PointCloud::Ptr merge_frames(const std::vector<Iso, Alloc>& poses, const std::vector<PointCloud::ConstPtr>& frames, double downsample_resolution, int target_num_points = 0) {
+  return merge_frames(std::vector<glim_b200::Pose>(poses.begin(), poses.end()), frames, downsample_resolution, target_num_points);
 }
 
 /// gtsam_points::VoxelBucket (standard_viewer_mem.cpp:77 takes its size): one 16-byte open-addressing slot {x, y, z, voxel index}
@@ -742,6 +760,11 @@ inline double overlap_gpu(const std::vector<GaussianVoxelMap::ConstPtr>& targets
   double ov = 0.0;
   glim_b200::check(gb_overlap(glim_b200::Context::of_stream(stream), maps.size(), maps.data(), s->handle(), T.data(), &ov), "gb_overlap");
   return ov;
+}
+/// the same with the container GLIM passes: std::vector<Eigen::Isometry3d> (odometry_estimation_gpu.cpp:225-231, :279)
+template <class Iso, class Alloc, class = std::enable_if_t<!std::is_same<Iso, glim_b200::Pose>::value && std::is_constructible<glim_b200::Pose, const Iso&>::value>>
+inline double overlap_gpu(const std::vector<GaussianVoxelMap::ConstPtr>& targets, const PointCloud::ConstPtr& source, const std::vector<Iso, Alloc>& deltas, CUstream_st* stream = nullptr) {
+  return overlap_gpu(targets, source, std::vector<glim_b200::Pose>(deltas.begin(), deltas.end()), stream);
 }
 /// gtsam_points::overlap_auto: GPU voxel maps dispatch to overlap_gpu (sub_mapping.cpp:252; global_mapping.cpp:322, :448)
 inline double overlap_auto(const GaussianVoxelMap::ConstPtr& target, const PointCloud::ConstPtr& source, const glim_b200::Pose& delta) { return overlap_gpu(target, source, delta); }

@@ -55,6 +55,32 @@ template <class Deskewing, class Iso, class V3, class V4> std::size_t deskew_lik
   return a.size() + b.size();
 }
 
+// GLIM's call sites hand Eigen::Isometry3d (and vectors of them) to the gtsam_points functions: the statements of
+// odometry_estimation_gpu.cpp:224-231, :247-248, :265, :279, sub_mapping.cpp:253, :486-496 and odometry_estimation_imu.cpp:313 with
+// the Eigen stand-in's Isometry3d against the SHIM's functions (compile-only; nothing is called).
+double eigen_typed_call_sites(const gtsam_points::GaussianVoxelMap::ConstPtr& voxelmap, const gtsam_points::PointCloud::ConstPtr& frame, CUstream_st* stream) {
+  const Eigen::Isometry3d T_world_a = Eigen::Isometry3d::Identity(), T_world_b = Eigen::Isometry3d::Identity();
+  std::vector<gtsam_points::GaussianVoxelMap::ConstPtr> keyframes_(2, voxelmap);
+  std::vector<Eigen::Isometry3d> delta_from_keyframes(keyframes_.size());
+  for (std::size_t i = 0; i < keyframes_.size(); i++) delta_from_keyframes[i] = T_world_a.inverse() * T_world_b;
+  double overlap = gtsam_points::overlap_gpu(keyframes_, frame, delta_from_keyframes, stream);
+  const Eigen::Isometry3d delta = T_world_a.inverse() * T_world_b;
+  overlap += gtsam_points::overlap_gpu(voxelmap, frame, delta, stream);
+  overlap += gtsam_points::overlap_gpu(voxelmap, frame, T_world_a.inverse() * T_world_b, stream);
+  overlap += gtsam_points::overlap_auto(voxelmap, frame, T_world_a.inverse() * T_world_b);
+  std::vector<Eigen::Isometry3d> poses_to_merge(2, T_world_a);
+  std::vector<gtsam_points::PointCloud::ConstPtr> keyframes_to_merge(2, frame);
+  gtsam_points::PointCloud::Ptr merged = gtsam_points::merge_frames(poses_to_merge, keyframes_to_merge, 0.1, 50000);
+  gtsam_points::PointCloudGPU::Ptr merged_gpu = gtsam_points::merge_frames_gpu(poses_to_merge, keyframes_to_merge, 0.1);
+  auto factor = std::make_shared<gtsam_points::IntegratedVGICPFactorGPU>(T_world_a, 1, voxelmap, frame, stream, nullptr);  // fixed target pose form (:161)
+  shim::CloudDeskewing deskewing;
+  const std::vector<double> times(2, 0.0);
+  const std::vector<shim::Vector4d> points(2);
+  const std::vector<Eigen::Isometry3d> pred_imu_poses(2, T_world_a);
+  const std::vector<shim::Vector4d> deskewed = deskewing.deskew(T_world_a, times, pred_imu_poses, 10.0, times, points);
+  return overlap + (double)merged->size() + (double)merged_gpu->size() + (double)deskewed.size() + (double)factor->dim();
+}
+
 template <class E> int regularization_names() { return (int)E::NONE + (int)E::PLANE + (int)E::NORMALIZED_MIN_EIG + (int)E::FROBENIUS; }
 
 int api_conformance() {
