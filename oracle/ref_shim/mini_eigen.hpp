@@ -15,6 +15,7 @@
 #include <vector>
 
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+#define EIGEN_WORLD_VERSION 3  // include/glim_b200/gtsam_points_compat.hpp keys its "points are Eigen types" branch on this macro
 
 namespace Eigen {
 
@@ -138,6 +139,8 @@ template <int BR, int BC, int R, int C> BlockRef<BR, BC, R, C>::operator Mat<BR,
   return b;
 }
 
+struct Vector3f { float a[3]; };  // device-side element types the shim only names (standard_viewer_mem.cpp:49-58)
+struct Matrix3f { float a[9]; };
 using Vector3d = Mat<3, 1>;
 using Vector4d = Mat<4, 1>;
 using Matrix3d = Mat<3, 3>;

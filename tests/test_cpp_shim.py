@@ -41,6 +41,10 @@ def test_shims_compile_standalone_and_gtsam_mode(tmp_path):
     subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{INC}", f"-I{os.path.join(CPP, 'gtsam_stub')}", "-c", os.path.join(CPP, "gtsam_mode_check.cpp"), "-o", str(tmp_path / "b.o")])
     subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-pthread", f"-I{INC}", "-c", os.path.join(CPP, "replay_glim.cpp"), "-o", str(tmp_path / "c.o")])
     subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{INC}", "-c", os.path.join(CPP, "preprocess_main.cpp"), "-o", str(tmp_path / "d.o")])
+    # GTSAM mode with Eigen-TYPED frames (the Eigen stand-in of oracle/ref_shim + the GTSAM signature stubs): the statements of GLIM's
+    # GPU call sites (odometry_estimation_gpu.cpp:76-106, :128-165, :224-248, :383-386; sub_mapping.cpp:165-169; global_mapping.cpp:252-266)
+    subprocess.check_call([GXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", f"-I{INC}", f"-I{os.path.join(CPP, 'gtsam_stub')}", f"-I{os.path.join(ROOT, 'oracle', 'ref_shim')}",
+                           "-c", os.path.join(CPP, "gtsam_eigen_mode_callsites.cpp"), "-o", str(tmp_path / "e.o")])
 
 
 def test_shim_api_matches_the_reference_headers(tmp_path):
