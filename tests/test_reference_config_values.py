@@ -65,3 +65,19 @@ def test_workload_builders_use_the_shipped_module_parameters():
     assert oc["vgicp_resolution"] == 0.5 and oc["vgicp_voxelmap_levels"] == 1 and oc["num_threads"] == 2
     w = workloads.sub_mapping_bundle(None, n_keyframes=3, n_rays=64 * 64, use_gpu=False)
     assert w.resolutions == [sm["keyframe_voxel_resolution"] * sm["keyframe_voxelmap_scaling_factor"] ** l for l in range(sm["keyframe_voxelmap_levels"])]
+
+
+def test_python_mirror_params_shipped_and_code_defaults():
+    from glim_b200 import preprocess
+
+    cfg = fixture()["config_preprocess"]["preprocess"]
+    s = preprocess.CloudPreprocessorParams.from_shipped_config()
+    assert (s.distance_near_thresh, s.distance_far_thresh, s.use_random_grid_downsampling, s.downsample_resolution, s.downsample_target, s.downsample_rate) == (
+        cfg["distance_near_thresh"], cfg["distance_far_thresh"], cfg["use_random_grid_downsampling"], cfg["downsample_resolution"], cfg["random_downsample_target"], cfg["random_downsample_rate"])
+    assert (s.enable_outlier_removal, s.outlier_removal_k, s.outlier_std_mul_factor, s.enable_cropbox_filter, s.crop_bbox_frame, s.k_correspondences) == (
+        cfg["enable_outlier_removal"], cfg["outlier_removal_k"], cfg["outlier_std_mul_factor"], cfg["enable_cropbox_filter"], cfg["crop_bbox_frame"], cfg["k_correspondences"])
+    assert list(s.crop_bbox_min) == cfg["crop_bbox_min"] and list(s.crop_bbox_max) == cfg["crop_bbox_max"]
+    # the CODE defaults (cloud_preprocessor.cpp:27-36, :58 -- what tests/test_oracle_vs_reference_tu.py reads back from the reference's
+    # own CloudPreprocessorParams constructor through an empty config)
+    d = preprocess.CloudPreprocessorParams()
+    assert (d.distance_near_thresh, d.distance_far_thresh, d.downsample_resolution, d.downsample_rate, d.outlier_std_mul_factor, d.k_correspondences) == (1.0, 100.0, 0.15, 0.3, 2.0, 8)
