@@ -131,3 +131,27 @@ REF_API int ref_preprocess(const ref_preprocess_params* P, double stamp, int n, 
   *scan_end_time = fr->scan_end_time;
   return m;
 }
+
+// ---- the stand-ins themselves, exposed so that tests can check them against numpy / scipy (they are OUR restatements of Eigen's and
+// GTSAM's published algorithms: tests/test_oracle_vs_reference_tu.py::test_stand_in_primitives_*) ----
+REF_API void ref_shim_eigen_sym3(const double* A9_colmajor, double* vals3, double* vecs9_colmajor) {
+  Eigen::Matrix3d m;
+  std::memcpy(m.a, A9_colmajor, sizeof(m.a));
+  Eigen::SelfAdjointEigenSolver<Eigen::Matrix3d> eig;
+  eig.computeDirect(m);
+  std::memcpy(vals3, eig.eigenvalues().a, 3 * sizeof(double));
+  std::memcpy(vecs9_colmajor, eig.eigenvectors().a, 9 * sizeof(double));
+}
+REF_API void ref_shim_slerp(const double* R0_colmajor, const double* R1_colmajor, double t, double* R_colmajor) {
+  Eigen::Matrix3d a, b;
+  std::memcpy(a.a, R0_colmajor, sizeof(a.a));
+  std::memcpy(b.a, R1_colmajor, sizeof(b.a));
+  const Eigen::Matrix3d r = Eigen::Quaterniond(a).slerp(t, Eigen::Quaterniond(b)).toRotationMatrix();
+  std::memcpy(R_colmajor, r.a, sizeof(r.a));
+}
+#include <gtsam/geometry/Pose3.h>
+REF_API void ref_shim_pose3_expmap(const double* xi6 /* omega, v */, double* T16_colmajor) {
+  gtsam::Vector6 xi;
+  std::memcpy(xi.a, xi6, sizeof(xi.a));
+  std::memcpy(T16_colmajor, gtsam::Pose3::Expmap(xi).matrix().a, 16 * sizeof(double));
+}

@@ -244,3 +244,51 @@ def test_preprocess_global_shutter_intensities_and_imu_crop_box(ref, frame):
     inside = (p_imu >= lo).all(1) & (p_imu <= hi).all(1)
     assert 0 < inside.sum() < len(base)
     assert np.array_equal(pts2[np.lexsort(pts2[:, :3].T)], base[~inside][np.lexsort(base[~inside][:, :3].T)])
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# The stand-ins are restatements too: check the three non-trivial ones against independent implementations, so that "the reference
+# file compiled against a stand-in" cannot hide a wrong stand-in.
+# ------------------------------------------------------------------------------------------------------------------------
+def test_stand_in_primitives_eigen_solver(ref):
+    rng = np.random.default_rng(11)
+    worst = 0.0
+    for trial in range(400):
+        Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        w = np.sort(rng.uniform(1e-4, 5.0, 3))
+        if trial % 5 == 0:
+            w[0] = w[1] * 1e-6  # a flat neighbourhood: smallest eigenvalue far below the others
+        A = (Q * w) @ Q.T
+        A = 0.5 * (A + A.T) * rng.choice([1e-3, 1.0, 1e3])
+        vals, vecs = np.zeros(3), np.zeros(9)
+        ref.ref_shim_eigen_sym3(_p(np.ascontiguousarray(A.T.reshape(9))), _p(vals), _p(vecs))
+        V = vecs.reshape(3, 3).T
+        ew, eV = np.linalg.eigh(A)
+        scale = np.abs(ew).max()
+        assert np.all(np.diff(vals) >= -1e-12 * scale)  # ascending, like Eigen
+        assert np.abs(vals - ew).max() < 1e-9 * scale
+        assert np.abs(V.T @ V - np.eye(3)).max() < 1e-9 and np.linalg.det(V) > 0  # orthonormal, right-handed (col1 = col2 x col0)
+        gap = np.min(np.diff(ew)) / scale
+        if gap > 1e-3:
+            err = max(min(np.abs(V[:, k] - eV[:, k]).max(), np.abs(V[:, k] + eV[:, k]).max()) for k in range(3))
+            worst = max(worst, err)
+    assert worst < 1e-9
+
+
+def test_stand_in_primitives_slerp_and_expmap(ref):
+    from scipy.spatial.transform import Rotation as Rot, Slerp
+
+    rng = np.random.default_rng(12)
+    for _ in range(200):
+        r0, r1 = Rot.from_rotvec(rng.normal(size=3) * rng.uniform(0, 2.5)), Rot.from_rotvec(rng.normal(size=3) * rng.uniform(0, 2.5))
+        t = float(rng.uniform(0, 1))
+        out = np.zeros(9)
+        ref.ref_shim_slerp.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        ref.ref_shim_slerp(_p(np.ascontiguousarray(r0.as_matrix().T.reshape(9))), _p(np.ascontiguousarray(r1.as_matrix().T.reshape(9))), t, _p(out))
+        want = Slerp([0, 1], Rot.from_matrix([r0.as_matrix(), r1.as_matrix()]))([t])[0].as_matrix()
+        assert np.abs(out.reshape(3, 3).T - want).max() < 1e-12
+    for _ in range(200):
+        xi = np.concatenate([rng.normal(size=3) * rng.choice([0.0, 1e-9, 0.3, 2.0]), rng.normal(size=3) * 3.0])
+        T = np.zeros(16)
+        ref.ref_shim_pose3_expmap(_p(xi), _p(T))
+        assert np.abs(T.reshape(4, 4).T - synth.se3_exp(xi)).max() < 1e-12  # synth.se3_exp: the closed form with the V(omega) matrix
