@@ -32,8 +32,9 @@ def test_library_is_sm100a_only_and_links_no_torch():
     if out.strip():
         archs = set(re.findall(r"sm_(\d+a?)", out))
         assert archs == {"100a"}, archs
-    ldd = os.popen(f"ldd {capi.SO_PATH}").read()
-    assert "torch" not in ldd and "c10" not in ldd
+    # library NAMES only: the load addresses ldd prints are random hex strings (ASLR) and may well contain "c10"
+    libs = [line.split()[0] for line in os.popen(f"ldd {capi.SO_PATH}").read().splitlines() if line.strip()]
+    assert libs and not [l for l in libs if "torch" in l or "c10" in l], libs
 
 
 def test_product_never_touches_the_oracle():
