@@ -70,7 +70,7 @@ def test_gauss_newton_registers_the_scans_cpu_factor(setup):
 finite = dict(allow_nan=False, allow_infinity=False)
 
 
-@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@settings(max_examples=25, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(st.tuples(st.floats(-3, 3, **finite), st.floats(-3, 3, **finite), st.floats(-0.5, 0.5, **finite)), st.floats(-np.pi, np.pi, **finite), st.floats(-0.2, 0.2, **finite), st.floats(-0.2, 0.2, **finite))
 def test_adjoint_identities_hold_at_arbitrary_poses(setup, t, yaw, pitch, roll):
     _, xyz1, cov1, maps, _, _ = setup
