@@ -18,8 +18,28 @@ def load(name):
     return json.loads(s)
 
 
+# only the parameters the hot path's call sites are constructed with (the rest of the files configures GLIM's optimizers, IMU
+# handling, logging ... -- out of scope)
+KEYS = {
+    "config_preprocess": ("preprocess", ["distance_near_thresh", "distance_far_thresh", "use_random_grid_downsampling", "downsample_resolution", "random_downsample_target", "random_downsample_rate",
+                                         "enable_outlier_removal", "outlier_removal_k", "outlier_std_mul_factor", "enable_cropbox_filter", "crop_bbox_frame", "crop_bbox_min", "crop_bbox_max", "k_correspondences"]),
+    "config_odometry_gpu": ("odometry_estimation", ["voxel_resolution", "voxel_resolution_max", "voxel_resolution_dmin", "voxel_resolution_dmax", "voxelmap_levels", "voxelmap_scaling_factor",
+                                                    "full_connection_window_size", "keyframe_update_strategy", "max_num_keyframes", "keyframe_min_overlap", "keyframe_max_overlap", "smoother_lag"]),
+    "config_odometry_cpu": ("odometry_estimation", ["registration_type", "vgicp_resolution", "vgicp_voxelmap_levels", "vgicp_voxelmap_scaling_factor", "num_threads"]),
+    "config_sub_mapping_gpu": ("sub_mapping", ["max_num_keyframes", "registration_error_factor_type", "keyframe_voxel_resolution", "keyframe_voxelmap_levels", "keyframe_voxelmap_scaling_factor",
+                                               "submap_downsample_resolution", "submap_voxel_resolution", "submap_target_num_points"]),
+    "config_global_mapping_gpu": ("global_mapping", ["registration_error_factor_type", "submap_voxel_resolution", "submap_voxel_resolution_max", "submap_voxelmap_levels", "submap_voxelmap_scaling_factor",
+                                                     "max_implicit_loop_distance", "min_implicit_loop_overlap"]),
+}
+
+
 def extract():
-    return {n: load(n) for n in FILES}
+    out = {}
+    for n in FILES:
+        section, keys = KEYS[n]
+        d = load(n)[section]
+        out[n] = {section: {k: d[k] for k in keys}}
+    return out
 
 
 if __name__ == "__main__":
