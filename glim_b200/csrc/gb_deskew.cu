@@ -143,7 +143,7 @@ extern "C" gb_status gb_deskew_pose_table(const double T_imu_lidar[16], const do
     if (!use_imu) {
       const double dt = tab[i];
       double w[3] = {0, 0, 0}, v[3] = {0, 0, 0};
-      if (n_imu == 0 && angular_vel && linear_vel) for (int k = 0; k < 3; k++) { w[k] = dt * angular_vel[k]; v[k] = dt * linear_vel[k]; }
+      if (n_imu == 0) for (int k = 0; k < 3; k++) { if (angular_vel) w[k] = dt * angular_vel[k]; if (linear_vel) v[k] = dt * linear_vel[k]; }  // either may be NULL = zero (glim_b200.h)
       T_l0_l1 = mul(mul(Tli, rigid_inverse(pose3_expmap(w, v))), Til);  // :41-42
     } else {
       const double time = stamp + tab[i];

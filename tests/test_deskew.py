@@ -91,6 +91,10 @@ def test_product_host_pose_table_matches_oracle():
     idx, Ts = preprocess.deskew_pose_table(T_IL, times, imu_times=IMU_T, imu_poses=IMU_P, stamp=100.0)
     assert np.array_equal(idx, idx_ref)
     assert np.allclose(np.einsum("nij,nj->ni", Ts[idx], pts), oracle.deskew_imu(T_IL, IMU_T, IMU_P, 100.0, times, pts), rtol=0, atol=1e-11)
+    for lv, av in ((V, None), (None, W)):  # either velocity may be omitted = zero (include/glim_b200.h)
+        idx, Ts = preprocess.deskew_pose_table(T_IL, times, linear_vel=lv, angular_vel=av)
+        want = oracle.deskew_const_vel(T_IL, np.zeros(3) if lv is None else lv, np.zeros(3) if av is None else av, times, pts)
+        assert np.allclose(np.einsum("nij,nj->ni", Ts[idx], pts), want, rtol=0, atol=1e-11)
     idx, Ts = preprocess.deskew_pose_table(T_IL, times)  # neither velocities nor poses: identity table
     assert np.allclose(Ts, np.eye(4), atol=1e-15)
     idx, Ts = preprocess.deskew_pose_table(T_IL, np.zeros(0))
