@@ -46,3 +46,24 @@ def test_global_mapping_gate_and_order():
     assert len(ov) == w.notes["num_pairs"] and min(ov.values()) >= 0.2
     for a, b in zip(f[0::2], f[1::2]):
         assert (a.target, a.source, a.pair) == (b.target, b.source, b.pair) and a.target < a.source
+
+
+def test_host_overlap_twin_equals_the_oracle():
+    """Workload.overlap without a context (the numpy twin that lets the reference arm and these tests run without the product
+    library) must be the oracle's overlap_gpu: fraction of transformed source points whose fp32 voxel is occupied in any target."""
+    from glim_b200 import synth
+    from oracle import oracle
+    from tests import util
+
+    w = workloads.sub_mapping_bundle(None, n_keyframes=4, n_rays=64 * 48)
+    packed = [oracle.pack_cloud(c[0], util.cov_colmajor16(c[1])) for c in w.host_clouds]
+    for level, res in enumerate(w.resolutions):
+        maps = [oracle.GpuMap(*packed[t], res) for t in range(3)]
+        for targets in ([0], [1, 2], [0, 1, 2]):
+            deltas = [synth.perturb(w.gt_delta(t, 3), synth.rng_for(7, t), 0.01, 0.05) for t in targets]
+            got = w.overlap(targets, level, 3, deltas)
+            # the twin transforms in fp64 and casts to fp32; the oracle (like the kernel) transforms in fp32 with explicit FMAs: a point
+            # on a voxel face may fall on the other side -- a handful of points out of thousands
+            want = oracle.overlap_gpumap([maps[t] for t in targets], packed[3][0], deltas)
+            assert abs(got - want) <= 5.0 / len(packed[3][0]), (targets, level, got, want)
+            assert 0.0 < want <= 1.0
